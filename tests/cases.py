@@ -1,0 +1,218 @@
+"""Shared parity cases.  Each case builds its ``tunable_params`` from a (schedulers,
+update_functions) namespace pair, so the same text runs on the reference's classes, on the
+oracle port and on the ns_gym_b200 descriptions compiled for the GPU.
+
+C1..C5 are the BASELINE.json configs; the rest widen opcode coverage.
+"""
+from __future__ import annotations
+
+MAP8 = {"map_name": "8x8"}
+
+
+def _c(env_id, params, wrapper=None, make=None, steps=60, fp32_rtol=None):
+    return dict(env_id=env_id, params=params, wrapper=wrapper or {}, make=make or {}, steps=steps)
+
+
+CASES = {
+    # ---- BASELINE configs --------------------------------------------------------------
+    "c1_cartpole_readme": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1),
+            "gravity": U.RandomWalk(S.PeriodicScheduler(period=3)),
+        },
+        wrapper=dict(change_notification=True), steps=120),
+    "c2_frozenlake8_stepchange": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionStepWiseUpdate(S.DiscreteScheduler({12}), [[0.0, 0.5, 0.5]])},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True),
+        make=dict(MAP8, max_episode_steps=200), steps=260),
+    "c2_frozenlake8_drift": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionDecrementUpdate(S.ContinuousScheduler(), k=0.05)},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True),
+        make=dict(MAP8, max_episode_steps=200), steps=120),
+    "c3_acrobot": _c(
+        "Acrobot-v1",
+        lambda S, U: {
+            "LINK_MASS_2": U.GeometricProgression(S.ContinuousScheduler(), r=1.001),
+            "LINK_LENGTH_1": U.IncrementUpdate(S.PeriodicScheduler(5), k=0.01),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=40),
+    "c3_mountaincar": _c(
+        "MountainCar-v0",
+        lambda S, U: {
+            "gravity": U.LinearInterpolation(S.ContinuousScheduler(), 0.0025, 0.0035, T=200),
+            "force": U.IncrementUpdate(S.ContinuousScheduler(), k=1e-5),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=230),
+    "c3_pendulum": _c(
+        "Pendulum-v1",
+        lambda S, U: {
+            "m": U.IncrementUpdate(S.ContinuousScheduler(), k=0.01),
+            "g": U.OscillatingUpdate(S.ContinuousScheduler(), delta=0.1),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=220),
+    "c5_bridge_uniform": _c(
+        "ns_gym/Bridge-v0",
+        lambda S, U: {"P": U.UniformDrift(S.ContinuousScheduler(), rate=0.05)},
+        wrapper=dict(initial_prob_dist=[0.9, 0.05, 0.05], change_notification=True,
+                     delta_change_notification=True), steps=130),
+    "c5_bridge_split": _c(
+        "ns_gym/Bridge-v0",
+        lambda S, U: {
+            "P_left": U.UniformDrift(S.ContinuousScheduler(), rate=0.05),
+            "P_right": U.DistributionDecrementUpdate(S.PeriodicScheduler(2), k=0.03),
+        },
+        wrapper=dict(initial_prob_dist=([0.9, 0.05, 0.05], [1.0, 0.0, 0.0]),
+                     change_notification=True, delta_change_notification=True), steps=130),
+    # ---- CartPole: every scalar opcode / scheduler ----------------------------------------
+    "cartpole_all_params": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "gravity": U.DeterministicTrend(S.BurstScheduler(2, 3), slope=0.01),
+            "masscart": U.PolynomialTrend(S.WindowScheduler([(2, 4), (10, 12)]), coeffs=[1e-3, 2e-4, -1e-5]),
+            "masspole": U.GeometricProgression(S.ContinuousScheduler(start=3, end=40), r=1.01),
+            "force_mag": U.ExponentialDecay(S.PeriodicScheduler(4), decay_rate=0.001),
+            "tau": U.SigmoidTransition(S.ContinuousScheduler(), a=0.02, b=0.03, k=0.5, t0=10),
+            "length": U.LinearInterpolation(S.DiscreteScheduler({1, 5, 9, 30}), 0.5, 0.8, T=25),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),
+    "cartpole_lists": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "gravity": U.StepWiseUpdate(S.PeriodicScheduler(2), [9.0, 10.5, 12.0]),
+            "length": U.CyclicUpdate(S.ContinuousScheduler(), [0.4, 0.5, 0.6, 0.55]),
+            "masscart": U.NoUpdate(S.PeriodicScheduler(3)),
+            "force_mag": U.OscillatingUpdate(S.ContinuousScheduler(), delta=0.5),
+            "masspole": U.DecrementUpdate(S.ContinuousScheduler(), k=0.004),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=90),
+    "cartpole_stochastic": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "gravity": U.RandomWalkWithDrift(S.ContinuousScheduler(), alpha=0.01, mu=0.0, sigma=0.2),
+            "force_mag": U.RandomWalkWithDriftAndTrend(S.PeriodicScheduler(2), alpha=-0.01, mu=0.1, sigma=0.3, slope=0.002),
+            "masspole": U.OrnsteinUhlenbeck(S.ContinuousScheduler(), theta=0.1, mu=0.2, sigma=0.01),
+            "length": U.OrnsteinUhlenbeck(S.ContinuousScheduler(), theta=0.05, mu=0.7),
+            "masscart": U.BoundedRandomWalk(S.ContinuousScheduler(), mu=0.0, sigma=0.2, lo=0.8, hi=1.2),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),
+    "cartpole_stochastic_scheds": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "gravity": U.IncrementUpdate(S.RandomScheduler(probability=0.3, seed=5), k=0.1),
+            "force_mag": U.IncrementUpdate(S.DecayingProbabilityScheduler(0.9, 0.05, seed=6), k=0.2),
+            "length": U.IncrementUpdate(S.MemorylessScheduler(p=0.25, seed=7), k=0.01),
+            "masscart": U.RandomWalk(S.RandomScheduler(probability=0.5, start=2, end=30, seed=8), mu=0, sigma=0.01),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),
+    "cartpole_constraint": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "masspole": U.DecrementUpdate(S.ContinuousScheduler(), k=0.03),
+            "gravity": U.DecrementUpdate(S.PeriodicScheduler(2), k=4.0),
+            "length": U.StepWiseUpdate(S.PeriodicScheduler(3), [-1.0, 0.6, 0.0, 0.7]),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=40),
+    "cartpole_silent": _c(
+        "CartPole-v1",
+        lambda S, U: {"masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)},
+        wrapper=dict(), steps=30),
+    "cartpole_persistent": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.001),
+            "gravity": U.CyclicUpdate(S.PeriodicScheduler(2), [9.0, 9.8, 10.5]),
+            "force_mag": U.RandomWalk(S.ContinuousScheduler(), mu=0, sigma=0.05),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True,
+                     persistent_params=True), steps=120),
+    "cartpole_custom_sched": _c(
+        "CartPole-v1",
+        lambda S, U: {
+            "gravity": U.IncrementUpdate(S.CustomScheduler(lambda t: t % 7 in (1, 2)), k=0.1),
+        },
+        wrapper=dict(change_notification=True), steps=60),
+    # ---- Acrobot / MountainCar / Pendulum extras ----------------------------------------------
+    "acrobot_constraints": _c(
+        "Acrobot-v1",
+        lambda S, U: {
+            "LINK_LENGTH_1": U.DecrementUpdate(S.ContinuousScheduler(), k=0.06),
+            "LINK_COM_POS_1": U.IncrementUpdate(S.PeriodicScheduler(3), k=0.05),
+            "LINK_LENGTH_2": U.DecrementUpdate(S.ContinuousScheduler(), k=0.2),
+            "LINK_COM_POS_2": U.IncrementUpdate(S.ContinuousScheduler(), k=0.07),
+            "LINK_MASS_1": U.DecrementUpdate(S.ContinuousScheduler(), k=0.15),
+            "dt": U.IncrementUpdate(S.PeriodicScheduler(4), k=0.01),
+            "LINK_MOI": U.GeometricProgression(S.ContinuousScheduler(), r=0.99),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=30),
+    "mountaincar_constraint": _c(
+        "MountainCar-v0",
+        lambda S, U: {
+            "gravity": U.DecrementUpdate(S.ContinuousScheduler(), k=0.0004),
+            "force": U.RandomWalk(S.ContinuousScheduler(), mu=0, sigma=0.0008),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=60),
+    "mountaincar_continuous": _c(
+        "MountainCarContinuous-v0",
+        lambda S, U: {"power": U.IncrementUpdate(S.ContinuousScheduler(), k=1e-5)},
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),
+    "pendulum_all": _c(
+        "Pendulum-v1",
+        lambda S, U: {
+            "m": U.GeometricProgression(S.ContinuousScheduler(), r=0.999),
+            "l": U.LinearInterpolation(S.ContinuousScheduler(), 1.0, 1.5, T=100),
+            "dt": U.DecrementUpdate(S.PeriodicScheduler(10), k=0.02),
+            "g": U.RandomWalk(S.PeriodicScheduler(2), mu=0, sigma=3.0),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=60),
+    # ---- gridworld extras ---------------------------------------------------------------------------
+    "frozenlake4_ops": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.TargetReversion(S.PeriodicScheduler(2), target=[0.4, 0.3, 0.3], theta=0.2)},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True,
+                     modified_rewards={"H": -1, "G": 1, "F": 0, "S": 0}), steps=150),
+    "frozenlake8_lerp": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionLinearInterpolation(
+            S.ContinuousScheduler(), [1.0, 0.0, 0.0], [0.2, 0.4, 0.4], T=30)},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True), make=dict(MAP8), steps=150),
+    "frozenlake8_cyclic_stale": _c(
+        # scheduler does not fire at t=0: exposes the stale-table-after-reset behaviour
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionCyclicUpdate(
+            S.ContinuousScheduler(start=3), [[0.5, 0.25, 0.25], [0.8, 0.1, 0.1], [0.0, 0.5, 0.5]])},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True), make=dict(MAP8), steps=200),
+    "frozenlake4_increment": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionIncrementUpdate(S.BurstScheduler(3, 2), k=0.07)},
+        wrapper=dict(initial_prob_dist=[0.4, 0.3, 0.3], change_notification=True,
+                     delta_change_notification=True), steps=120),
+    "frozenlake4_noupdate": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionNoUpdate(S.PeriodicScheduler(2))},
+        wrapper=dict(initial_prob_dist=[0.6, 0.2, 0.2], change_notification=True,
+                     delta_change_notification=True), steps=60),
+    "bridge_stepwise": _c(
+        "ns_gym/Bridge-v0",
+        lambda S, U: {"P": U.DistributionStepWiseUpdate(
+            S.PeriodicScheduler(4), [[0.8, 0.1, 0.1], [0.6, 0.2, 0.2], [0.34, 0.33, 0.33]])},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True), steps=130),
+    "cliff_drift": _c(
+        "CliffWalking-v1",
+        lambda S, U: {"P": U.DistributionDecrementUpdate(S.ContinuousScheduler(), k=0.02)},
+        wrapper=dict(initial_prob_dist=[1, 0, 0, 0], change_notification=True,
+                     delta_change_notification=True), make=dict(max_episode_steps=50), steps=120),
+    "cliff_terminal": _c(
+        "CliffWalking-v1",
+        lambda S, U: {"P": U.UniformDrift(S.PeriodicScheduler(3), rate=0.1)},
+        wrapper=dict(initial_prob_dist=[0.7, 0.1, 0.1, 0.1], change_notification=True,
+                     delta_change_notification=True, terminal_cliff=True), steps=120),
+}
