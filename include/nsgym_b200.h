@@ -1,0 +1,248 @@
+/* nsgym_b200.h -- C ABI of the B200-native batched simulator for ns_gym's
+ * non-stationary env-step path.
+ *
+ * The reference has no FFI on this path: the boundary is a pure-Python object protocol,
+ *   NSClassicControlWrapper.step   ns_gym/wrappers/classic_control.py:60-100
+ *   NSFrozenLakeWrapper.step       ns_gym/wrappers/toy_text.py:342-380
+ *   NSCliffWalkingWrapper.step     ns_gym/wrappers/toy_text.py:162-193
+ *   NSBridgeWrapper.step           ns_gym/wrappers/toy_text.py:633-651
+ *   NSWrapper.step / reset         ns_gym/base.py:296-410
+ *   UpdateFn.__call__              ns_gym/base.py:124-149
+ *   Scheduler.__call__             ns_gym/base.py:67-81
+ * This header is the boundary a maintainer would bind (ctypes stub: INTEGRATION.md):
+ * the wrapper's `tunable_params` dict is lowered on the host to one NsgymSlot per bound
+ * parameter (scheduler opcode + update opcode + coefficients), and one kernel launch
+ * advances every env of the batch by one step.
+ *
+ * Conventions
+ *  - every `d_` pointer is a DEVICE pointer owned by the caller (a torch tensor); the
+ *    library never frees caller memory.  `h_` pointers are host memory (pinned for speed).
+ *  - every compute call takes a cudaStream_t (passed as void*) and is asynchronous unless
+ *    stated; a handle is not thread-safe.
+ *  - return value: 0 = OK, negative = error; text via nsgym_last_error().
+ *  - SoA layout, N = number of envs of this handle, w = 4 (NSGYM_F32) or 8 (NSGYM_F64):
+ *      state   classic control: one packed vector per env, real[N][S] (S = 4 or 2),
+ *              16/32-byte aligned so a thread moves it with 128-bit accesses;
+ *              gridworlds: int32[N] (cell index)
+ *      theta   real[P][N]   one plane per BOUND scalar parameter (classic control);
+ *              double[P*D][N] for gridworlds (D = 3 or 4 probabilities per parameter,
+ *              always fp64 so the cumulative-sum comparisons are bit-exact)
+ *      t       int32[N]; bits 0..27 episode time, bit 31 = episode ended at the last call
+ *              (consumed by next-step autoreset), bit 30 = CartPole "already terminated
+ *              once" (reward 0 on further steps), bit 29 = gridworld "P table rebuilt
+ *              since the last reset" (stale-table rule)
+ *      istate  int32[I][N]  list cursors / Memoryless next-fire time, I = nsgym layout
+ *      action  int32[N] (discrete) or real[N] (Pendulum, MountainCarContinuous)
+ *      reward  float[N];  flags uint8[N];  change uint8[N] (bit j = slot j changed);
+ *      delta   real[P][N] (double for gridworlds) or NULL;  obs float[N][O] or NULL
+ */
+#ifndef NSGYM_B200_H
+#define NSGYM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define NSGYM_ABI_VERSION 1
+#define NSGYM_MAX_SLOTS 8
+#define NSGYM_MAX_THETA 8
+#define NSGYM_MAX_DIST 4
+
+/* ---- env kinds (reference class: ns_gym/base.py:611-635, envs/Bridge.py) ---- */
+enum {
+  NSGYM_ENV_CARTPOLE = 0,        /* CartPoleEnv   theta: gravity masscart masspole force_mag tau length */
+  NSGYM_ENV_ACROBOT = 1,         /* AcrobotEnv    theta: dt L1 L2 M1 M2 COM1 COM2 MOI */
+  NSGYM_ENV_MOUNTAINCAR = 2,     /* MountainCarEnv theta: gravity force */
+  NSGYM_ENV_MOUNTAINCAR_CONT = 3,/* Continuous_MountainCarEnv theta: power */
+  NSGYM_ENV_PENDULUM = 4,        /* PendulumEnv   theta: m l dt g */
+  NSGYM_ENV_FROZENLAKE = 5,      /* FrozenLakeEnv theta: P */
+  NSGYM_ENV_CLIFFWALKING = 6,    /* CliffWalkingEnv theta: P (4 outcomes) */
+  NSGYM_ENV_BRIDGE = 7,          /* Bridge        theta: P | P_left, P_right */
+  NSGYM_ENV_COUNT = 8
+};
+
+enum { NSGYM_F32 = 0, NSGYM_F64 = 1 };
+
+/* autoreset: NONE = caller resets (single-env semantics, stepping past the end allowed);
+ * NEXT_STEP = gymnasium 1.x vector default: an env that ended at call k is reset by call
+ * k+1 (action ignored, reward 0, flags = NSGYM_FLAG_RESET only). */
+enum { NSGYM_AUTORESET_NONE = 0, NSGYM_AUTORESET_NEXT_STEP = 1 };
+
+enum {
+  NSGYM_FLAG_TERMINATED = 1,
+  NSGYM_FLAG_TRUNCATED = 2,
+  NSGYM_FLAG_RESET = 4,          /* this call performed the autoreset of the env */
+  NSGYM_FLAG_BAD_DIST = 128      /* gridworld: negative weight / sum != 1 (reference raises) */
+};
+
+/* ---- scheduler opcodes (ns_gym/schedulers.py) ---- */
+enum {
+  NSGYM_SCHED_CONTINUOUS = 0,    /* :46-53   always */
+  NSGYM_SCHED_PERIODIC = 1,      /* :77-89   t % si[0] == 0 */
+  NSGYM_SCHED_BITMAP = 2,        /* :56-74 Discrete, :31-43 Custom pre-evaluated; bit t of bitmap[si[0]..], si[1] bits */
+  NSGYM_SCHED_BURST = 3,         /* :119-140 (t % si[1]) < si[0] */
+  NSGYM_SCHED_WINDOW = 4,        /* :180-198 any pool_i[si[0]+2k] <= t <= pool_i[si[0]+2k+1], k < si[1] */
+  NSGYM_SCHED_RANDOM = 5,        /* :9-28    u < sf[0] */
+  NSGYM_SCHED_DECAY = 6,         /* :143-177 u < sf[0] * exp(-sf[1] t) */
+  NSGYM_SCHED_MEMORYLESS = 7,    /* :92-116  t == istate; istate = t + Geom(sf[0]); first time si[0] */
+  NSGYM_SCHED_COUNT = 8
+};
+
+/* ---- update opcodes (update_functions/single_param.py, distribution.py) ---- */
+enum {
+  NSGYM_UPD_NOP = 0,             /* NoUpdate :226-240 */
+  NSGYM_UPD_ADD = 1,             /* Increment :154-175 (uf0 = k), Decrement :178-199 (uf0 = -k) */
+  NSGYM_UPD_ADD_T = 2,           /* DeterministicTrend :20-40   y + uf0 * t */
+  NSGYM_UPD_POLY = 3,            /* PolynomialTrend :451-473    coeffs pool_f[ui0..ui0+ui1) */
+  NSGYM_UPD_MUL = 4,             /* GeometricProgression :290-307 */
+  NSGYM_UPD_MUL_EXP = 5,         /* ExponentialDecay :266-287   y * exp(-uf0 t) */
+  NSGYM_UPD_ADD_SIN = 6,         /* OscillatingUpdate :243-264  y + uf0 sin t */
+  NSGYM_UPD_SIGMOID = 7,         /* SigmoidTransition :349-385  uf = a, b-a, k, t0 */
+  NSGYM_UPD_LERP = 8,            /* LinearInterpolation :476-508 uf = s, e-s, T */
+  NSGYM_UPD_STEPWISE = 9,        /* StepWiseUpdate :202-223     values pool_f[ui0..ui0+ui1), cursor istate */
+  NSGYM_UPD_CYCLIC = 10,         /* CyclicUpdate :388-408 */
+  NSGYM_UPD_RW = 11,             /* RandomWalk :84-113, WithDrift :116-151, WithDriftAndTrend :43-81; uf = alpha, mu, sigma, slope */
+  NSGYM_UPD_OU = 12,             /* OrnsteinUhlenbeck :310-346  uf = theta, mu, sigma */
+  NSGYM_UPD_BRW = 13,            /* BoundedRandomWalk :411-448  uf = mu, sigma, lo, hi */
+  /* distribution opcodes (distribution.py) */
+  NSGYM_UPD_D_NOP = 32,          /* :217-231 */
+  NSGYM_UPD_D_INC = 33,          /* :41-67   uf0 = k */
+  NSGYM_UPD_D_DEC = 34,          /* :70-97   uf0 = k */
+  NSGYM_UPD_D_UNIFORM = 35,      /* :234-261 uf0 = 1-rate, uf1 = rate * (1/n) */
+  NSGYM_UPD_D_TARGET = 36,       /* :264-293 uf0 = theta, uf1..4 = target */
+  NSGYM_UPD_D_LERP = 37,         /* :296-331 uf0 = T, pool_f[ui0..] = start[D], (end-start)[D] */
+  NSGYM_UPD_D_STEPWISE = 38,     /* :100-130 ui1 distributions of D doubles at pool_f[ui0..] */
+  NSGYM_UPD_D_CYCLIC = 39        /* :334-356 */
+};
+
+/* ---- constraint rules (wrappers/classic_control.py:193-422) ---- */
+enum {
+  NSGYM_CONS_NONE = 0,
+  NSGYM_CONS_REJECT_LE0 = 1,     /* reject new <= 0 */
+  NSGYM_CONS_REJECT_LT0 = 2,     /* reject new <  0 */
+  NSGYM_CONS_ACRO_LENGTH1 = 3,   /* :241-265  <=0 | new partner COM > new | new < current COM */
+  NSGYM_CONS_ACRO_COM = 4        /* :307-357  <=0 | new partner LEN < new | new > current LEN */
+};
+
+typedef struct {
+  int32_t sched_op;
+  int32_t upd_op;
+  int32_t theta_index;           /* which physical parameter (order of the kind's list above) */
+  int32_t constraint;
+  int32_t start;                 /* inclusive; INT32_MAX = never in range */
+  int32_t end;                   /* inclusive; INT32_MAX = +inf */
+  int32_t si[4];
+  int32_t ui[4];
+  int32_t partner_slot;          /* Acrobot cross-checks: slot of the partner parameter or -1 */
+  int32_t partner_index;         /* theta index of the partner parameter */
+  int32_t istate_plane;          /* plane of this slot in istate[][] or -1 */
+  int32_t istate_init;           /* cursor 0 / first Memoryless time */
+  double sf[2];
+  double uf[6];
+} NsgymSlot;
+
+typedef struct {
+  int32_t abi_version;           /* NSGYM_ABI_VERSION */
+  int32_t env_kind;
+  int32_t precision;             /* NSGYM_F32 | NSGYM_F64 (classic control only) */
+  int32_t autoreset;
+  int64_t n_envs;                /* envs owned by THIS handle (one shard) */
+  int64_t env_id_offset;         /* global id of local env 0: Philox keys use global ids */
+  uint64_t seed;
+  int32_t max_episode_steps;     /* TimeLimit; <= 0: none */
+  int32_t persistent_params;     /* base.py:381-395 */
+  int32_t n_slots;
+  int32_t n_dist;                /* gridworlds: probabilities per parameter (3 | 4), else 0 */
+  NsgymSlot slots[NSGYM_MAX_SLOTS];
+  double theta_init[NSGYM_MAX_THETA][NSGYM_MAX_DIST]; /* per theta_index; scalars use [i][0] */
+  /* pools referenced by the slots (host pointers, copied at create) */
+  const double* pool_f; int32_t n_pool_f;
+  const int32_t* pool_i; int32_t n_pool_i;
+  const uint32_t* bitmap; int32_t n_bitmap_words;
+  /* gridworld description (toy_text.py:426-469, :86-138; envs/Bridge.py:12,113-174) */
+  int32_t nrow, ncol;
+  uint64_t hole_mask, goal_mask, start_mask; /* bit = cell index; nrow*ncol <= 64 */
+  int32_t start_cell;
+  int32_t split_mode;            /* Bridge: P_left / P_right by column of the current cell */
+  float reward_f, reward_h, reward_g, reward_s; /* by destination cell letter */
+  int32_t terminal_cliff;        /* CliffWalking */
+  int32_t _reserved;
+} NsgymSpec;
+
+typedef struct {                 /* bytes the caller must allocate for each bound buffer */
+  size_t state, theta, t, istate, action, reward, flags, change, delta, obs;
+  int32_t state_words, obs_words, n_istate, theta_planes;
+  double bytes_per_step;         /* algorithmic bytes per env-step, delta & obs as bound */
+} NsgymLayout;
+
+typedef struct {
+  void* d_state; void* d_theta; int32_t* d_t; int32_t* d_istate;
+  void* d_action;                /* staging used by nsgym_step_host */
+  float* d_reward; uint8_t* d_flags; uint8_t* d_change;
+  void* d_delta;                 /* NULL: delta not produced */
+  float* d_obs;                  /* NULL: obs not produced (fp32 CartPole/MountainCar: obs == state) */
+} NsgymBuffers;
+
+typedef struct {                 /* host-side results of nsgym_step_host; NULL members are skipped */
+  float* h_reward; uint8_t* h_flags; uint8_t* h_change; void* h_delta;
+  void* h_state;                 /* classic control: packed state (fp32: the observation itself); gridworld: int32 cell */
+  float* h_obs;
+} NsgymHostOut;
+
+typedef struct NsgymHandle NsgymHandle;
+
+int nsgym_abi_version(void);
+size_t nsgym_sizeof(int which);  /* 0 NsgymSlot, 1 NsgymSpec, 2 NsgymLayout, 3 NsgymBuffers, 4 NsgymHostOut */
+const char* nsgym_last_error(void);
+
+/* replaces: wrapper construction (base.py:222-294, classic_control.py:27-58, toy_text.py:28-84,282-340,547-603) */
+int nsgym_create(const NsgymSpec* spec, NsgymHandle** out);
+void nsgym_destroy(NsgymHandle* h);
+int nsgym_layout(const NsgymHandle* h, int want_delta, int want_obs, NsgymLayout* out);
+int nsgym_bind(NsgymHandle* h, const NsgymBuffers* buffers);
+
+/* replaces: NSWrapper.reset + subclass resets (base.py:365-431, classic_control.py:102-109,
+ * toy_text.py:202-210,382-399,653-667).  d_mask NULL = all envs, else uint8[N] (non-zero = reset).
+ * d_inj_uniform NULL = native Philox draws, else double[L][N] (lanes: oracle/streams.py). */
+int nsgym_reset(NsgymHandle* h, const uint8_t* d_mask, const double* d_inj_uniform, void* stream);
+
+/* replaces: <wrapper>.step (file:line list at the top).  d_action NULL = the bound staging
+ * buffer.  d_inj_uniform double[L][N] / d_inj_normal double[P][N] or NULL (native Philox).
+ * skip_updates != 0 = planning env with in_sim_change False (classic_control.py:70-75). */
+int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform,
+               const double* d_inj_normal, int skip_updates, void* stream);
+
+/* Same call with HOST buffers: copies actions host->device, steps, copies the requested
+ * results device->host, in `n_chunks` pipelined chunks, and returns after the last copy has
+ * completed (synchronous).  This is the end-to-end call a host-side agent loop makes. */
+int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* out, int n_chunks);
+
+/* K fused steps with state, theta and cursors in registers under a device-side policy
+ * (MCTS-style random rollouts, benchmark_algorithms/MCTS.py:162-181).  policy 0 = uniform
+ * random action.  d_return float[N] += sum of rewards (discounted by gamma^k);
+ * d_length int32[N] += steps taken before the first episode end.  With
+ * NSGYM_AUTORESET_NEXT_STEP envs keep cycling through episodes inside the K steps. */
+int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d_return,
+                  int32_t* d_length, int skip_updates, void* stream);
+
+/* Fire-test + advance stages only (a1 + a2/a3), for known-answer checks of the update
+ * functions: applies slot `slot` to d_param (real[N] scalars, or double[D][N]) at times
+ * d_time[N]; writes new values in place, d_flag uint8[N], d_delta real[N]. */
+int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_time,
+                      int32_t* d_istate, uint8_t* d_flag, void* d_delta,
+                      const double* d_inj_uniform, const double* d_inj_normal, int64_t n,
+                      void* stream);
+
+/* replaces: reset(seed=...) reseeding (base.py:386-388, 412-421): re-keys the Philox streams */
+void nsgym_set_seed(NsgymHandle* h, uint64_t seed);
+uint64_t nsgym_step_index(const NsgymHandle* h);        /* Philox counter (launches so far) */
+void nsgym_set_step_index(NsgymHandle* h, uint64_t v);
+int64_t nsgym_launch_count(const NsgymHandle* h);       /* kernels launched by this handle */
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NSGYM_B200_H */

@@ -10,7 +10,14 @@ from . import base, schedulers, update_functions  # noqa: F401
 
 __version__ = "0.1.0"
 
-_LAZY = {"compile", "native", "vector_env", "wrappers", "distributed", "configs"}
+_LAZY = {"compile", "native", "vector_env", "wrappers", "distributed", "build"}
+
+
+def make(env_id: str, num_envs: int = 1, **kwargs):
+    """Batched stand-in for ``gym.make``: see ``ns_gym_b200.wrappers.make``."""
+    from .wrappers import make as _make
+
+    return _make(env_id, num_envs, **kwargs)
 
 
 def __getattr__(name):

@@ -1,0 +1,98 @@
+"""Build ``libnsgym_b200.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU).
+
+Four translation units, compiled in parallel:
+
+* ``nsgym_f32.cu``        fp32 fast-mode classic-control kernels (FMA contraction on)
+* ``nsgym_f64.cu``        fp64 parity-mode kernels, ``-fmad=false`` (NumPy rounds every op)
+* ``nsgym_gridworld.cu``  gridworld kernels, ``-fmad=false`` (fp64 cumulative sums / W1)
+* ``nsgym_abi.cu``        the C ABI (host code)
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+CSRC = os.path.join(HERE, "csrc")
+INCLUDE = os.path.join(ROOT, "include")
+LIB_DIR = os.path.join(HERE, "_lib")
+LIB_PATH = os.path.join(LIB_DIR, "libnsgym_b200.so")
+OBJ_DIR = os.path.join(LIB_DIR, "obj")
+
+ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
+COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
+          "--expt-relaxed-constexpr"]
+UNITS = {
+    "nsgym_f32.cu": [],
+    "nsgym_f64.cu": ["-fmad=false"],
+    "nsgym_gridworld.cu": ["-fmad=false"],
+    "nsgym_abi.cu": [],
+}
+
+
+def _nvcc() -> str:
+    for cand in (os.environ.get("NVCC"), shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
+        if cand and os.path.exists(cand):
+            return cand
+    raise RuntimeError("nvcc not found: ns_gym_b200 needs the CUDA toolkit to build its kernels")
+
+
+def _source_digest() -> str:
+    h = hashlib.sha256()
+    files = sorted(os.listdir(CSRC)) + ["../../include/nsgym_b200.h"]
+    for name in files:
+        path = os.path.normpath(os.path.join(CSRC, name))
+        if os.path.isfile(path):
+            h.update(name.encode())
+            with open(path, "rb") as f:
+                h.update(f.read())
+    h.update(repr((ARCH, COMMON, UNITS)).encode())
+    return h.hexdigest()
+
+
+def is_current() -> bool:
+    stamp = LIB_PATH + ".sha256"
+    if not (os.path.exists(LIB_PATH) and os.path.exists(stamp)):
+        return False
+    with open(stamp) as f:
+        return f.read().strip() == _source_digest()
+
+
+def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
+    """Compile and link the shared library; returns its path.  No-op when up to date."""
+    if not force and is_current():
+        return LIB_PATH
+    nvcc = _nvcc()
+    os.makedirs(OBJ_DIR, exist_ok=True)
+
+    def compile_unit(item):
+        name, extra = item
+        obj = os.path.join(OBJ_DIR, name.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, name), "-o", obj]
+        if ptxas_info:
+            cmd[1:1] = ["-Xptxas", "-v"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed on {name}:\n{r.stdout}\n{r.stderr}")
+        if verbose or ptxas_info:
+            sys.stderr.write(r.stderr)
+        return obj
+
+    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
+        objs = list(pool.map(compile_unit, UNITS.items()))
+    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH, *objs]
+    r = subprocess.run(link, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    with open(LIB_PATH + ".sha256", "w") as f:
+        f.write(_source_digest())
+    return LIB_PATH
+
+
+if __name__ == "__main__":
+    print(build_library(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))

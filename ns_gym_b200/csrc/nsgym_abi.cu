@@ -1,0 +1,371 @@
+// nsgym_abi.cu -- the C ABI of include/nsgym_b200.h: handle life cycle, buffer layout,
+// launches, and the host-buffer (end-to-end) step pipeline.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+
+#include "nsgym_host.h"
+
+namespace {
+
+thread_local std::string g_error;
+
+int fail(int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  g_error = buf;
+  return code;
+}
+
+#define NSG_CUDA(call)                                                                       \
+  do {                                                                                       \
+    cudaError_t e__ = (call);                                                                \
+    if (e__ != cudaSuccess) return fail(-10, "%s: %s", #call, cudaGetErrorString(e__));      \
+  } while (0)
+
+constexpr int kHostStreams = 4;
+
+struct KindInfo { int state_words, obs_words, n_theta; bool box; };
+const KindInfo kKinds[NSGYM_ENV_COUNT] = {
+    {4, 4, 6, false}, {4, 6, 8, false}, {2, 2, 2, false}, {2, 2, 1, true},
+    {2, 3, 4, true},  {1, 0, 1, false}, {1, 0, 1, false}, {1, 0, 3, false},
+};
+
+}  // namespace
+
+struct NsgymHandle {
+  NsgymSpec spec;
+  nsg::DevicePools pools{nullptr, nullptr, nullptr};
+  NsgymBuffers buf{};
+  bool bound = false;
+  bool initialised = false;
+  uint64_t step_index = 0;
+  int64_t launches = 0;
+  int n_istate = 0;
+  cudaStream_t streams[kHostStreams]{};
+  bool streams_ready = false;
+
+  bool grid() const { return nsg::is_grid_kind(spec.env_kind); }
+  size_t real_bytes() const { return grid() ? 8 : (spec.precision == NSGYM_F64 ? 8 : 4); }
+  size_t action_bytes() const { return kKinds[spec.env_kind].box ? real_bytes() : 4; }
+  size_t state_bytes_per_env() const {
+    return grid() ? 4 : size_t(kKinds[spec.env_kind].state_words) * real_bytes();
+  }
+  int theta_planes() const { return grid() ? spec.n_slots * spec.n_dist : spec.n_slots; }
+};
+
+namespace {
+
+nsg::LaunchIO base_io(const NsgymHandle* h) {
+  nsg::LaunchIO io{};
+  io.state = h->buf.d_state; io.theta = h->buf.d_theta; io.t = h->buf.d_t; io.istate = h->buf.d_istate;
+  io.action = h->buf.d_action;
+  io.reward = h->buf.d_reward; io.flags = h->buf.d_flags; io.change = h->buf.d_change;
+  io.delta = h->buf.d_delta; io.obs = h->buf.d_obs;
+  io.n = h->spec.n_envs; io.begin = 0; io.count = h->spec.n_envs;
+  io.gid_offset = uint64_t(h->spec.env_id_offset); io.seed = h->spec.seed; io.step_index = h->step_index;
+  io.gamma = 1.f;
+  return io;
+}
+
+cudaError_t dispatch(NsgymHandle* h, nsg::LaunchOp op, const nsg::LaunchIO& io, cudaStream_t s) {
+  h->launches += 1;
+  if (h->grid()) return nsg::launch_grid(op, h->spec, h->pools, io, s);
+  if (h->spec.precision == NSGYM_F64) return nsg::launch_classic_f64(op, h->spec, h->pools, io, s);
+  return nsg::launch_classic_f32(op, h->spec, h->pools, io, s);
+}
+
+int validate(const NsgymSpec* s) {
+  if (!s) return fail(-1, "spec is NULL");
+  if (s->abi_version != NSGYM_ABI_VERSION)
+    return fail(-1, "ABI version mismatch: caller %d, library %d", s->abi_version, NSGYM_ABI_VERSION);
+  if (s->env_kind < 0 || s->env_kind >= NSGYM_ENV_COUNT) return fail(-1, "unknown env_kind %d", s->env_kind);
+  if (s->n_envs <= 0) return fail(-1, "n_envs must be positive");
+  if (s->n_slots < 0 || s->n_slots > NSGYM_MAX_SLOTS) return fail(-1, "n_slots %d out of range", s->n_slots);
+  const KindInfo& k = kKinds[s->env_kind];
+  if (s->n_slots > k.n_theta) return fail(-1, "%d slots > %d tunable parameters of this env", s->n_slots, k.n_theta);
+  const bool grid = nsg::is_grid_kind(s->env_kind);
+  if (grid) {
+    const int want = s->env_kind == NSGYM_ENV_CLIFFWALKING ? 4 : 3;
+    if (s->n_dist != want) return fail(-1, "n_dist %d, this env needs %d", s->n_dist, want);
+    if (s->nrow <= 0 || s->ncol <= 0 || s->nrow * s->ncol > 64)
+      return fail(-1, "gridworld maps are limited to 64 cells (got %dx%d)", s->nrow, s->ncol);
+    const int inv = (65536 + s->ncol - 1) / s->ncol;
+    for (int c = 0; c < s->nrow * s->ncol; ++c)
+      if (((c * inv) >> 16) != c / s->ncol) return fail(-1, "internal: reciprocal division inexact");
+    if (s->start_cell < 0 || s->start_cell >= s->nrow * s->ncol) return fail(-1, "start_cell out of range");
+    if (s->env_kind != NSGYM_ENV_BRIDGE && s->n_slots != 1) return fail(-1, "this env has exactly one parameter, P");
+  } else if (s->precision != NSGYM_F32 && s->precision != NSGYM_F64) {
+    return fail(-1, "precision must be NSGYM_F32 or NSGYM_F64");
+  }
+  for (int j = 0; j < s->n_slots; ++j) {
+    const NsgymSlot& sl = s->slots[j];
+    if (sl.theta_index < 0 || sl.theta_index >= k.n_theta) return fail(-1, "slot %d: theta_index out of range", j);
+    for (int q = 0; q < j; ++q)
+      if (s->slots[q].theta_index == sl.theta_index) return fail(-1, "slot %d: parameter bound twice", j);
+    if (sl.sched_op < 0 || sl.sched_op >= NSGYM_SCHED_COUNT) return fail(-1, "slot %d: bad sched_op", j);
+    const bool dist_op = sl.upd_op >= NSGYM_UPD_D_NOP;
+    if (dist_op != grid) return fail(-1, "slot %d: update opcode %d does not fit this env kind", j, sl.upd_op);
+    if (sl.sched_op == NSGYM_SCHED_PERIODIC && sl.si[0] <= 0) return fail(-1, "slot %d: period must be > 0", j);
+    if (sl.sched_op == NSGYM_SCHED_BURST && sl.si[1] <= 0) return fail(-1, "slot %d: burst cycle must be > 0", j);
+    if (sl.sched_op == NSGYM_SCHED_BITMAP &&
+        (sl.si[0] < 0 || (sl.si[0] + (sl.si[1] + 31) / 32) > s->n_bitmap_words))
+      return fail(-1, "slot %d: bitmap range outside the pool", j);
+    if (sl.sched_op == NSGYM_SCHED_WINDOW && (sl.si[0] < 0 || sl.si[0] + 2 * sl.si[1] > s->n_pool_i))
+      return fail(-1, "slot %d: window list outside the pool", j);
+    const int per = dist_op ? s->n_dist : 1;
+    switch (sl.upd_op) {
+      case NSGYM_UPD_POLY: case NSGYM_UPD_STEPWISE: case NSGYM_UPD_CYCLIC:
+      case NSGYM_UPD_D_STEPWISE: case NSGYM_UPD_D_CYCLIC:
+        if (sl.ui[0] < 0 || sl.ui[1] < 0 || sl.ui[0] + sl.ui[1] * per > s->n_pool_f)
+          return fail(-1, "slot %d: value list outside the pool", j);
+        if ((sl.upd_op == NSGYM_UPD_CYCLIC || sl.upd_op == NSGYM_UPD_D_CYCLIC) && sl.ui[1] == 0)
+          return fail(-1, "slot %d: cyclic list is empty", j);
+        break;
+      case NSGYM_UPD_D_LERP:
+        if (sl.ui[0] < 0 || sl.ui[0] + 2 * per > s->n_pool_f) return fail(-1, "slot %d: lerp data outside the pool", j);
+        break;
+      default: break;
+    }
+  }
+  return 0;
+}
+
+template <typename T>
+int upload(const T* src, int n, const T** dst) {
+  *dst = nullptr;
+  if (n <= 0 || !src) return 0;
+  T* d = nullptr;
+  NSG_CUDA(cudaMalloc(&d, sizeof(T) * size_t(n)));
+  NSG_CUDA(cudaMemcpy(d, src, sizeof(T) * size_t(n), cudaMemcpyHostToDevice));
+  *dst = d;
+  return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+int nsgym_abi_version(void) { return NSGYM_ABI_VERSION; }
+
+size_t nsgym_sizeof(int which) {
+  switch (which) {
+    case 0: return sizeof(NsgymSlot);
+    case 1: return sizeof(NsgymSpec);
+    case 2: return sizeof(NsgymLayout);
+    case 3: return sizeof(NsgymBuffers);
+    case 4: return sizeof(NsgymHostOut);
+    default: return 0;
+  }
+}
+
+const char* nsgym_last_error(void) { return g_error.c_str(); }
+
+int nsgym_create(const NsgymSpec* spec, NsgymHandle** out) {
+  if (!out) return fail(-1, "out is NULL");
+  *out = nullptr;
+  if (int rc = validate(spec)) return rc;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(-2, "no CUDA device: ns_gym_b200 has no CPU execution path");
+  NsgymHandle* h = new (std::nothrow) NsgymHandle();
+  if (!h) return fail(-3, "out of host memory");
+  h->spec = *spec;
+  int planes = 0;
+  for (int j = 0; j < spec->n_slots; ++j)
+    if (spec->slots[j].istate_plane >= 0) planes = planes > spec->slots[j].istate_plane + 1 ? planes : spec->slots[j].istate_plane + 1;
+  h->n_istate = planes;
+  int rc = upload(spec->pool_f, spec->n_pool_f, &h->pools.pool_f);
+  if (!rc) rc = upload(spec->pool_i, spec->n_pool_i, &h->pools.pool_i);
+  if (!rc) rc = upload(spec->bitmap, spec->n_bitmap_words, &h->pools.bitmap);
+  if (rc) { nsgym_destroy(h); return rc; }
+  h->spec.pool_f = nullptr; h->spec.pool_i = nullptr; h->spec.bitmap = nullptr;
+  *out = h;
+  return 0;
+}
+
+void nsgym_destroy(NsgymHandle* h) {
+  if (!h) return;
+  cudaFree(const_cast<double*>(h->pools.pool_f));
+  cudaFree(const_cast<int32_t*>(h->pools.pool_i));
+  cudaFree(const_cast<uint32_t*>(h->pools.bitmap));
+  if (h->streams_ready)
+    for (auto& s : h->streams) cudaStreamDestroy(s);
+  delete h;
+}
+
+int nsgym_layout(const NsgymHandle* h, int want_delta, int want_obs, NsgymLayout* out) {
+  if (!h || !out) return fail(-1, "NULL argument");
+  const KindInfo& k = kKinds[h->spec.env_kind];
+  const size_t n = size_t(h->spec.n_envs), w = h->real_bytes();
+  std::memset(out, 0, sizeof *out);
+  out->state = n * h->state_bytes_per_env();
+  out->theta = n * size_t(h->theta_planes()) * w;
+  out->t = n * 4;
+  out->istate = n * size_t(h->n_istate) * 4;
+  out->action = n * h->action_bytes();
+  out->reward = n * 4;
+  out->flags = n;
+  out->change = n;
+  out->delta = want_delta ? n * size_t(h->spec.n_slots) * w : 0;
+  out->obs = (want_obs && k.obs_words) ? n * size_t(k.obs_words) * 4 : 0;
+  out->state_words = k.state_words;
+  out->obs_words = k.obs_words;
+  out->n_istate = h->n_istate;
+  out->theta_planes = h->theta_planes();
+  // algorithmic bytes per env-step: state r+w, bound theta r+w, action r, t r+w,
+  // reward w, flags w, change w [+ obs w] [+ delta w] [+ cursor planes r+w]
+  double b = 2.0 * double(h->state_bytes_per_env()) + 2.0 * double(h->theta_planes()) * double(w) +
+             double(h->action_bytes()) + 8.0 + 4.0 + 1.0 + 1.0;
+  if (out->obs) b += 4.0 * k.obs_words;
+  if (out->delta) b += double(h->spec.n_slots) * double(w);
+  b += 8.0 * h->n_istate;
+  out->bytes_per_step = b;
+  return 0;
+}
+
+int nsgym_bind(NsgymHandle* h, const NsgymBuffers* b) {
+  if (!h || !b) return fail(-1, "NULL argument");
+  if (!b->d_state || !b->d_t || !b->d_action || !b->d_reward || !b->d_flags || !b->d_change)
+    return fail(-1, "state, t, action, reward, flags and change buffers are mandatory");
+  if (h->theta_planes() > 0 && !b->d_theta) return fail(-1, "theta buffer is mandatory when parameters are bound");
+  if (h->n_istate > 0 && !b->d_istate) return fail(-1, "istate buffer is mandatory for list / Memoryless slots");
+  if ((reinterpret_cast<uintptr_t>(b->d_state) & 31u) != 0) return fail(-1, "state buffer must be 32-byte aligned");
+  h->buf = *b;
+  h->bound = true;
+  h->initialised = false;
+  return 0;
+}
+
+int nsgym_reset(NsgymHandle* h, const uint8_t* d_mask, const double* d_inj_uniform, void* stream) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  if (!h->initialised && d_mask) return fail(-1, "the first reset must cover all envs (mask must be NULL)");
+  nsg::LaunchIO io = base_io(h);
+  io.mask = d_mask;
+  io.inj_u = d_inj_uniform;
+  io.force_init = h->initialised ? 0 : 1;
+  cudaError_t e = dispatch(h, nsg::OP_RESET, io, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-10, "reset launch: %s", cudaGetErrorString(e));
+  h->initialised = true;
+  h->step_index += 1;
+  return 0;
+}
+
+int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform, const double* d_inj_normal,
+               int skip_updates, void* stream) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  if (!h->initialised) return fail(-4, "step before reset");
+  nsg::LaunchIO io = base_io(h);
+  if (d_action) io.action = d_action;
+  io.inj_u = d_inj_uniform;
+  io.inj_z = d_inj_normal;
+  io.skip_updates = skip_updates;
+  cudaError_t e = dispatch(h, nsg::OP_STEP, io, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-10, "step launch: %s", cudaGetErrorString(e));
+  h->step_index += 1;
+  return 0;
+}
+
+int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* out, int n_chunks) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  if (!h->initialised) return fail(-4, "step before reset");
+  if (!h_action || !out) return fail(-1, "NULL argument");
+  if (!h->streams_ready) {
+    for (auto& s : h->streams) NSG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    h->streams_ready = true;
+  }
+  const int64_t n = h->spec.n_envs;
+  if (n_chunks < 1) n_chunks = 1;
+  if (n_chunks > n) n_chunks = int(n);
+  // chunk boundaries on multiples of 256 envs keep every sub-range 128-byte aligned
+  int64_t per = ((n + n_chunks - 1) / n_chunks + 255) / 256 * 256;
+  const size_t ab = h->action_bytes(), sb = h->state_bytes_per_env(), w = h->real_bytes();
+  const int obs_words = kKinds[h->spec.env_kind].obs_words;
+  int c = 0;
+  for (int64_t b = 0; b < n; b += per, ++c) {
+    const int64_t cnt = (n - b) < per ? (n - b) : per;
+    cudaStream_t s = h->streams[c % kHostStreams];
+    NSG_CUDA(cudaMemcpyAsync(static_cast<char*>(h->buf.d_action) + size_t(b) * ab,
+                             static_cast<const char*>(h_action) + size_t(b) * ab, size_t(cnt) * ab,
+                             cudaMemcpyHostToDevice, s));
+    nsg::LaunchIO io = base_io(h);
+    io.begin = b;
+    io.count = cnt;
+    cudaError_t e = dispatch(h, nsg::OP_STEP, io, s);
+    if (e != cudaSuccess) return fail(-10, "step launch: %s", cudaGetErrorString(e));
+    if (out->h_reward)
+      NSG_CUDA(cudaMemcpyAsync(out->h_reward + b, h->buf.d_reward + b, size_t(cnt) * 4, cudaMemcpyDeviceToHost, s));
+    if (out->h_flags)
+      NSG_CUDA(cudaMemcpyAsync(out->h_flags + b, h->buf.d_flags + b, size_t(cnt), cudaMemcpyDeviceToHost, s));
+    if (out->h_change)
+      NSG_CUDA(cudaMemcpyAsync(out->h_change + b, h->buf.d_change + b, size_t(cnt), cudaMemcpyDeviceToHost, s));
+    if (out->h_state)
+      NSG_CUDA(cudaMemcpyAsync(static_cast<char*>(out->h_state) + size_t(b) * sb,
+                               static_cast<char*>(h->buf.d_state) + size_t(b) * sb, size_t(cnt) * sb,
+                               cudaMemcpyDeviceToHost, s));
+    if (out->h_obs && h->buf.d_obs && obs_words)
+      NSG_CUDA(cudaMemcpyAsync(out->h_obs + b * obs_words, h->buf.d_obs + b * obs_words,
+                               size_t(cnt) * obs_words * 4, cudaMemcpyDeviceToHost, s));
+    if (out->h_delta && h->buf.d_delta)
+      for (int j = 0; j < h->spec.n_slots; ++j)
+        NSG_CUDA(cudaMemcpyAsync(static_cast<char*>(out->h_delta) + (size_t(j) * n + b) * w,
+                                 static_cast<char*>(h->buf.d_delta) + (size_t(j) * n + b) * w, size_t(cnt) * w,
+                                 cudaMemcpyDeviceToHost, s));
+  }
+  for (auto& s : h->streams) NSG_CUDA(cudaStreamSynchronize(s));
+  h->step_index += 1;
+  return 0;
+}
+
+int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d_return, int32_t* d_length,
+                  int skip_updates, void* stream) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  if (!h->initialised) return fail(-4, "rollout before reset");
+  if (policy != 0) return fail(-1, "only policy 0 (uniform random) is implemented");
+  if (k_steps <= 0) return fail(-1, "k_steps must be positive");
+  nsg::LaunchIO io = base_io(h);
+  io.k_steps = k_steps;
+  io.gamma = gamma;
+  io.ret = d_return;
+  io.len = d_length;
+  io.skip_updates = skip_updates;
+  cudaError_t e = dispatch(h, nsg::OP_ROLLOUT, io, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-10, "rollout launch: %s", cudaGetErrorString(e));
+  h->step_index += uint64_t(k_steps);
+  return 0;
+}
+
+int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_time, int32_t* d_istate,
+                      uint8_t* d_flag, void* d_delta, const double* d_inj_uniform, const double* d_inj_normal,
+                      int64_t n, void* stream) {
+  if (!h) return fail(-1, "NULL handle");
+  if (slot < 0 || slot >= h->spec.n_slots) return fail(-1, "slot out of range");
+  if (!d_param || !d_time || !d_flag) return fail(-1, "NULL argument");
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  h->launches += 1;
+  if (h->grid())
+    e = nsg::launch_eval_dist(h->spec, h->pools, slot, static_cast<double*>(d_param), d_time, d_istate, d_flag,
+                              static_cast<double*>(d_delta), d_inj_uniform, n, h->spec.seed, h->step_index, s);
+  else if (h->spec.precision == NSGYM_F64)
+    e = nsg::launch_eval_scalar_f64(h->spec, h->pools, slot, d_param, d_time, d_istate, d_flag, d_delta,
+                                    d_inj_uniform, d_inj_normal, n, h->spec.seed, h->step_index, s);
+  else
+    e = nsg::launch_eval_scalar_f32(h->spec, h->pools, slot, d_param, d_time, d_istate, d_flag, d_delta,
+                                    d_inj_uniform, d_inj_normal, n, h->spec.seed, h->step_index, s);
+  if (e != cudaSuccess) return fail(-10, "eval launch: %s", cudaGetErrorString(e));
+  h->step_index += 1;
+  return 0;
+}
+
+void nsgym_set_seed(NsgymHandle* h, uint64_t seed) { if (h) h->spec.seed = seed; }
+uint64_t nsgym_step_index(const NsgymHandle* h) { return h ? h->step_index : 0; }
+void nsgym_set_step_index(NsgymHandle* h, uint64_t v) { if (h) h->step_index = v; }
+int64_t nsgym_launch_count(const NsgymHandle* h) { return h ? h->launches : 0; }
+
+}  // extern "C"

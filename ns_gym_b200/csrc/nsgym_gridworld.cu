@@ -1,0 +1,69 @@
+// Gridworld kernels (FrozenLake / CliffWalking / Bridge).  Probabilities are always fp64 and
+// this unit is built with -fmad=false: cumulative sums and W1 distances match NumPy exactly.
+#include "nsgym_grid.cuh"
+#include "nsgym_classic_launch.cuh"
+
+namespace nsg {
+
+template <int MAXP>
+static GridProgram<MAXP> build_grid_program(const NsgymSpec& spec, const DevicePools& pools) {
+  GridProgram<MAXP> G{};
+  G.base = build_program<double, MAXP>(spec, pools);
+  for (int i = 0; i < 3; ++i)
+    for (int k = 0; k < NSGYM_MAX_DIST; ++k) G.dist_init[i][k] = spec.theta_init[i][k];
+  G.hole_mask = spec.hole_mask; G.goal_mask = spec.goal_mask; G.start_mask = spec.start_mask;
+  G.nrow = spec.nrow; G.ncol = spec.ncol;
+  G.inv_ncol = (65536 + spec.ncol - 1) / spec.ncol;
+  G.start_cell = spec.start_cell;
+  G.n_dist = spec.n_dist; G.split_mode = spec.split_mode; G.terminal_cliff = spec.terminal_cliff;
+  G.reward_f = spec.reward_f; G.reward_h = spec.reward_h; G.reward_g = spec.reward_g; G.reward_s = spec.reward_s;
+  return G;
+}
+
+template <int KIND, int D, int MAXP>
+static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& a,
+                                 cudaStream_t stream) {
+  if (spec.n_slots > MAXP || spec.n_dist != D) return cudaErrorInvalidValue;
+  const GridProgram<MAXP> G = build_grid_program<MAXP>(spec, pools);
+  const StepIO<double> io = build_io<double>(a);
+  const int block = 256;
+  const unsigned grid = unsigned((a.count + block - 1) / block);
+  if (grid == 0) return cudaSuccess;
+  switch (op) {
+    case OP_STEP: grid_step_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
+    case OP_RESET: grid_reset_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
+    case OP_ROLLOUT:
+      grid_rollout_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io, a.k_steps, a.gamma, a.ret, a.len);
+      break;
+  }
+  return cudaGetLastError();
+}
+
+cudaError_t launch_grid(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& io,
+                        cudaStream_t stream) {
+  switch (spec.env_kind) {
+    case NSGYM_ENV_FROZENLAKE: return launch_grid_k<NSGYM_ENV_FROZENLAKE, 3, 1>(op, spec, pools, io, stream);
+    case NSGYM_ENV_CLIFFWALKING: return launch_grid_k<NSGYM_ENV_CLIFFWALKING, 4, 1>(op, spec, pools, io, stream);
+    case NSGYM_ENV_BRIDGE: return launch_grid_k<NSGYM_ENV_BRIDGE, 3, 2>(op, spec, pools, io, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
+cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, int slot, double* param,
+                             const int32_t* time, int32_t* istate, uint8_t* flag, double* delta,
+                             const double* inj_u, int64_t n, uint64_t seed, uint64_t step_index,
+                             cudaStream_t stream) {
+  const GridProgram<2> G = build_grid_program<2>(spec, pools);
+  const int block = 256;
+  const unsigned grid = unsigned((n + block - 1) / block);
+  if (grid == 0) return cudaSuccess;
+  if (spec.n_dist == 4)
+    eval_dist_update_kernel<4, 2><<<grid, block, 0, stream>>>(G, slot, param, time, istate, flag, delta, inj_u, n,
+                                                              seed, step_index);
+  else
+    eval_dist_update_kernel<3, 2><<<grid, block, 0, stream>>>(G, slot, param, time, istate, flag, delta, inj_u, n,
+                                                              seed, step_index);
+  return cudaGetLastError();
+}
+
+}  // namespace nsg

@@ -1,0 +1,299 @@
+"""Batched non-stationary env on one GPU: the host-side mirror of the reference's wrapper
+stack (``NSWrapper.step / reset``, ``ns_gym/base.py:296-410``) over the C ABI.
+
+One ``NSVectorEnv`` owns N envs of one kind (one shard).  All per-env data lives in torch
+tensors on the device (SoA, ``include/nsgym_b200.h``); one call to ``step`` is one kernel
+launch.  ``step`` returns gymnasium-vector style batched results with the reference's
+observation dict ``{"state", "env_change", "delta_change", "relative_time"}`` and the same
+notification gating (``base.py:323-341``); ``step_raw`` is the same launch without building
+the Python result (results stay in ``env.buffers``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Any, Optional
+
+import numpy as np
+import torch
+
+from . import native as nv
+from .base import Reward
+from .compile import BOX_ACTION, N_ACTIONS, CompiledProgram, compile_program
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+class NSVectorEnv:
+    def __init__(self, env_id: str, tunable_params: dict, num_envs: int, *,
+                 change_notification: bool = False, delta_change_notification: bool = False,
+                 in_sim_change: bool = False, scalar_reward: bool = True,
+                 persistent_params: bool = False, precision: str = "fp32",
+                 autoreset: str = "next_step", seed: int = 0, env_id_offset: int = 0,
+                 device: Any = None, want_obs: Optional[bool] = None, want_delta: Optional[bool] = None,
+                 **env_kwargs):
+        if delta_change_notification:                         # base.py:252-255
+            assert change_notification, (
+                "If change_notification is True, delta_change_notification must be True")
+        if not torch.cuda.is_available():
+            raise nv.NsgymError("ns_gym_b200 needs a CUDA device: there is no CPU execution path")
+        self.lib = nv.load()
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.num_envs = int(num_envs)
+        self.program: CompiledProgram = compile_program(
+            env_id, tunable_params, num_envs, precision=precision, autoreset=autoreset, seed=seed,
+            env_id_offset=env_id_offset, persistent_params=persistent_params, **env_kwargs)
+        self.keys = list(self.program.keys)
+        self.change_notification = change_notification
+        self.delta_change_notification = delta_change_notification
+        self.in_sim_change = in_sim_change
+        self.scalar_reward = scalar_reward
+        self.persistent_params = persistent_params
+        self.frozen = False
+        self.is_sim_env = False
+        self.has_reset = False
+        self.precision = precision if not self.program.is_grid else "fp64"
+        self.real = torch.float64 if self.program.spec.precision == nv.F64 else torch.float32
+
+        with torch.cuda.device(self.device):
+            h = C.c_void_p()
+            nv.check(self.lib.nsgym_create(C.byref(self.program.spec), C.byref(h)), "nsgym_create")
+            self._h = h
+            kind = self.program.env_kind
+            if want_obs is None:
+                # fp32 CartPole / MountainCar: the observation IS the stored state
+                want_obs = (not self.program.is_grid) and (
+                    self.real == torch.float64 or self.program.obs_words != self.program.state_words)
+            if want_delta is None:
+                want_delta = delta_change_notification
+            lay = nv.NsgymLayout()
+            nv.check(self.lib.nsgym_layout(self._h, int(want_delta), int(want_obs), C.byref(lay)), "nsgym_layout")
+            self.layout = lay
+            self.bytes_per_step = float(lay.bytes_per_step)
+            n, dev = self.num_envs, self.device
+            b: dict[str, Optional[torch.Tensor]] = {}
+            if self.program.is_grid:
+                b["state"] = torch.zeros(n, dtype=torch.int32, device=dev)
+            else:
+                b["state"] = torch.zeros((n, lay.state_words), dtype=self.real, device=dev)
+            b["theta"] = (torch.zeros((lay.theta_planes, n), dtype=self.real, device=dev)
+                          if lay.theta_planes else None)
+            b["t"] = torch.zeros(n, dtype=torch.int32, device=dev)
+            b["istate"] = torch.zeros((lay.n_istate, n), dtype=torch.int32, device=dev) if lay.n_istate else None
+            b["action"] = torch.zeros(n, dtype=self.real if kind in BOX_ACTION else torch.int32, device=dev)
+            b["reward"] = torch.zeros(n, dtype=torch.float32, device=dev)
+            b["flags"] = torch.zeros(n, dtype=torch.uint8, device=dev)
+            b["change"] = torch.zeros(n, dtype=torch.uint8, device=dev)
+            b["delta"] = (torch.zeros((len(self.keys), n), dtype=self.real, device=dev)
+                          if (want_delta and self.keys) else None)
+            b["obs"] = (torch.zeros((n, lay.obs_words), dtype=torch.float32, device=dev)
+                        if lay.obs else None)
+            self.buffers = b
+            cb = nv.NsgymBuffers(
+                d_state=b["state"].data_ptr(), d_theta=0 if b["theta"] is None else b["theta"].data_ptr(),
+                d_t=b["t"].data_ptr(), d_istate=0 if b["istate"] is None else b["istate"].data_ptr(),
+                d_action=b["action"].data_ptr(), d_reward=b["reward"].data_ptr(),
+                d_flags=b["flags"].data_ptr(), d_change=b["change"].data_ptr(),
+                d_delta=0 if b["delta"] is None else b["delta"].data_ptr(),
+                d_obs=0 if b["obs"] is None else b["obs"].data_ptr())
+            nv.check(self.lib.nsgym_bind(self._h, C.byref(cb)), "nsgym_bind")
+        self._zeros_u8 = torch.zeros(n, dtype=torch.uint8, device=self.device)
+        self._zeros_real = torch.zeros(n, dtype=self.real, device=self.device)
+
+    # ------------------------------------------------------------------------------------
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and getattr(self, "lib", None) is not None:
+            try:
+                self.lib.nsgym_destroy(h)
+            except Exception:
+                pass
+            self._h = None
+
+    close = __del__
+
+    def _stream(self):
+        return C.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    @property
+    def skip_updates(self) -> bool:
+        """Planning env with ``in_sim_change`` False: theta is frozen (classic_control.py:70-75)."""
+        return self.is_sim_env and not self.in_sim_change
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.nsgym_launch_count(self._h))
+
+    @property
+    def action_space_n(self):
+        return N_ACTIONS.get(self.program.env_kind)
+
+    # ------------------------------------------------------------------------------------
+    def reset(self, *, seed: Optional[int] = None, options=None, mask: Optional[torch.Tensor] = None,
+              inject_uniform: Optional[torch.Tensor] = None):
+        """``NSWrapper.reset`` for the batch (``base.py:365-410``).  ``seed`` re-keys the
+        Philox streams (every env's stream is keyed by (seed, global env id))."""
+        with torch.cuda.device(self.device):
+            if seed is not None:
+                self.lib.nsgym_set_seed(self._h, int(seed) & (2**64 - 1))
+            m = None
+            if mask is not None:
+                m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
+            nv.check(self.lib.nsgym_reset(self._h, _ptr(m), _ptr(inject_uniform), self._stream()), "nsgym_reset")
+        self.has_reset = True
+        n_keys = len(self.keys)
+        zeros_c = {k: self._zeros_u8 for k in self.keys}
+        zeros_d = {k: self._zeros_real for k in self.keys}
+        obs = {"state": self.observation(), "env_change": zeros_c, "delta_change": zeros_d,
+               "relative_time": self.relative_time()}
+        info = {"Ground Truth Env Change": dict(zeros_c), "Ground Truth Delta Change": dict(zeros_d)}
+        del n_keys
+        return obs, info
+
+    def step_raw(self, actions: Optional[torch.Tensor] = None, inject_uniform=None, inject_normal=None):
+        """One kernel launch; results stay in ``self.buffers``."""
+        nv.check(self.lib.nsgym_step(self._h, _ptr(actions), _ptr(inject_uniform), _ptr(inject_normal),
+                                     int(self.skip_updates), self._stream()), "nsgym_step")
+
+    def step(self, actions, inject_uniform=None, inject_normal=None):
+        """``<wrapper>.step`` for the batch -> ``(obs, reward, terminated, truncated, info)``."""
+        want = self.buffers["action"]
+        if not torch.is_tensor(actions):
+            actions = torch.as_tensor(np.asarray(actions))
+        actions = actions.to(device=self.device, dtype=want.dtype).reshape(self.num_envs).contiguous()
+        with torch.cuda.device(self.device):
+            self.step_raw(actions, inject_uniform, inject_normal)
+        return self._package()
+
+    # ---- result packaging (NSWrapper.step, base.py:314-363) ----
+    def observation(self) -> torch.Tensor:
+        b = self.buffers
+        if b["obs"] is not None:
+            return b["obs"]
+        return b["state"]
+
+    def relative_time(self) -> torch.Tensor:
+        return self.buffers["t"] & nv.T_TIME_MASK
+
+    def ground_truth_change(self) -> dict:
+        c = self.buffers["change"]
+        return {k: (c >> j) & 1 for j, k in enumerate(self.keys)}
+
+    def ground_truth_delta(self) -> dict:
+        d = self.buffers["delta"]
+        if d is None:
+            return {k: None for k in self.keys}
+        return {k: d[j] for j, k in enumerate(self.keys)}
+
+    def _package(self):
+        b = self.buffers
+        flags = b["flags"]
+        terminated = (flags & nv.FLAG_TERMINATED) != 0
+        truncated = (flags & nv.FLAG_TRUNCATED) != 0
+        muted = self.frozen or (self.is_sim_env and not self.in_sim_change)
+        gt_c = self.ground_truth_change()
+        gt_d = self.ground_truth_delta()
+        zc = {k: self._zeros_u8 for k in self.keys}
+        zd = {k: self._zeros_real for k in self.keys}
+        env_change = zc if (not self.change_notification or muted) else gt_c
+        delta_change = zd if (not self.delta_change_notification or muted) else gt_d
+        rel = self.relative_time()
+        obs = {"state": self.observation(), "env_change": env_change, "delta_change": delta_change,
+               "relative_time": rel}
+        reward: Any = b["reward"]
+        if not self.scalar_reward:
+            reward = Reward(reward=b["reward"], env_change=env_change, delta_change=delta_change,
+                            relative_time=rel)
+        info = {"Ground Truth Env Change": gt_c, "Ground Truth Delta Change": gt_d,
+                "was_reset": (flags & nv.FLAG_RESET) != 0}
+        if self.program.is_grid:
+            info["transition_prob"] = self.transition_prob()
+        else:
+            info["prob"] = 1.0                                   # classic_control.py:98
+        return obs, reward, terminated, truncated, info
+
+    # ---- parameter views ----
+    def theta(self) -> dict:
+        """Current value of every bound parameter: ``{name: tensor[N]}`` (scalars) or
+        ``{name: tensor[D, N]}`` (slip distributions, the wrapper's ``transition_prob``)."""
+        th = self.buffers["theta"]
+        if not self.program.is_grid:
+            return {k: th[j] for j, k in enumerate(self.keys)}
+        return self.transition_prob()
+
+    def transition_prob(self) -> dict:
+        """``transition_prob`` of the gridworld wrappers (toy_text.py:178-187, 362-373).  For
+        FrozenLake / CliffWalking the stored planes are the probabilities baked into the
+        sampling table; until the first fire after a reset the wrapper's ``transition_prob``
+        is the initial distribution (stale-table rule)."""
+        th, D = self.buffers["theta"], self.program.n_dist
+        out = {}
+        for j, k in enumerate(self.keys):
+            planes = th[j * D:(j + 1) * D]
+            if self.program.env_kind != nv.ENV_BRIDGE:
+                fresh = (self.buffers["t"] & nv.T_TABLE_FRESH) != 0
+                idx = self.program.spec.slots[j].theta_index
+                init = torch.tensor([self.program.spec.theta_init[idx][q] for q in range(D)],
+                                    dtype=torch.float64, device=self.device)[:, None]
+                planes = torch.where(fresh[None, :], planes, init)
+            out[k] = planes
+        return out
+
+    # ---- fused K-step rollout ----
+    def rollout(self, k_steps: int, gamma: float = 1.0, returns: Optional[torch.Tensor] = None,
+                lengths: Optional[torch.Tensor] = None):
+        """K fused steps under the device-side uniform-random policy, state in registers."""
+        if returns is None:
+            returns = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
+        if lengths is None:
+            lengths = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_rollout(self._h, int(k_steps), 0, float(gamma), _ptr(returns), _ptr(lengths),
+                                            int(self.skip_updates), self._stream()), "nsgym_rollout")
+        return returns, lengths
+
+    # ---- host-buffer (end-to-end) step through the C ABI ----
+    def make_host_io(self, want_state: bool = True):
+        """Pinned host buffers for ``step_host``: (actions, outputs dict)."""
+        b = self.buffers
+        pin = dict(pin_memory=True)
+        act = torch.zeros(self.num_envs, dtype=b["action"].dtype, **pin)
+        out = {"reward": torch.zeros(self.num_envs, dtype=torch.float32, **pin),
+               "flags": torch.zeros(self.num_envs, dtype=torch.uint8, **pin),
+               "change": torch.zeros(self.num_envs, dtype=torch.uint8, **pin)}
+        if b["obs"] is not None:
+            out["obs"] = torch.zeros(tuple(b["obs"].shape), dtype=torch.float32, **pin)
+        elif want_state:
+            out["state"] = torch.zeros(tuple(b["state"].shape), dtype=b["state"].dtype, **pin)
+        return act, out
+
+    def step_host(self, h_actions: torch.Tensor, h_out: dict, n_chunks: int = 8):
+        """``nsgym_step_host``: actions host->device, step, results device->host (synchronous)."""
+        ho = nv.NsgymHostOut(
+            h_reward=h_out["reward"].data_ptr(), h_flags=h_out["flags"].data_ptr(),
+            h_change=h_out["change"].data_ptr() if "change" in h_out else 0,
+            h_delta=0, h_state=h_out["state"].data_ptr() if "state" in h_out else 0,
+            h_obs=h_out["obs"].data_ptr() if "obs" in h_out else 0)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_step_host(self._h, C.c_void_p(h_actions.data_ptr()), C.byref(ho),
+                                              int(n_chunks)), "nsgym_step_host")
+
+    def host_bytes_per_step(self, h_actions: torch.Tensor, h_out: dict):
+        h2d = h_actions.numel() * h_actions.element_size()
+        d2h = sum(t.numel() * t.element_size() for t in h_out.values())
+        return h2d, d2h
+
+    # ---- notification control (base.py:443-458) ----
+    def freeze(self, mode: bool = True):
+        if not isinstance(mode, bool):
+            raise TypeError(f"Expected mode to be a boolean, got {type(mode)}")
+        self.frozen = mode
+        return self
+
+    def unfreeze(self):
+        return self.freeze(False)
+
+    def get_default_params(self):
+        from .base import TUNABLE_PARAMS
+        return TUNABLE_PARAMS[self.program.env_class]

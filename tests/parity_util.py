@@ -1,0 +1,103 @@
+"""Helpers shared by the parity tests: run a case on the oracle port / the CUDA path and
+compare traces.  A trace is the dict produced by ``oracle.vector.trace`` (arrays [K, N, ...])."""
+from __future__ import annotations
+
+import numpy as np
+
+from oracle import harness, vector
+
+INT_KEYS = ("terminated", "truncated", "was_reset", "relative_time", "env_change", "gt_change")
+# stated tolerances (north_star): deterministic paths 1e-9 relative in fp64 mode
+FP64_RTOL, FP64_ATOL = 1e-9, 1e-12
+
+
+def n_slots_of(case):
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    return len(case["params"](PS, PU))
+
+
+def oracle_trace(case, n_envs, seed, steps=None, actions=None):
+    K = steps or case["steps"]
+    if actions is None:
+        actions = harness.draw_actions(case, seed + 1, K, n_envs)
+    clock, per_env, u, z = harness.make_streams(seed, n_envs, K + 1, n_slots_of(case))
+    envs = harness.port_envs(case, n_envs, per_env)
+    tr = vector.trace(vector.SyncVector(envs, per_env, clock), actions)
+    return tr, actions, u, z
+
+
+def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_step"):
+    """Same trace from the CUDA path with the same injected tables."""
+    import torch
+
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.vector_env import NSVectorEnv
+    from ns_gym_b200 import native as nv
+
+    tp = case["params"](PS, PU)
+    env = NSVectorEnv(case["env_id"], tp, n_envs, precision=precision, autoreset=autoreset,
+                      want_delta=True, want_obs=True, **case.get("wrapper", {}), **case.get("make", {}))
+    dev = env.device
+    U = torch.as_tensor(u, dtype=torch.float64, device=dev).contiguous()
+    Z = torch.as_tensor(z, dtype=torch.float64, device=dev).contiguous()
+    K = len(actions)
+    keys = env.keys
+    D = env.program.n_dist if env.program.is_grid else 1
+
+    def raw_state():
+        s = env.buffers["state"]
+        return s.double().cpu().numpy() if not env.program.is_grid else s.cpu().numpy().astype(np.int64)
+
+    def obs_state():
+        o = env.observation()
+        return o.cpu().numpy() if not env.program.is_grid else o.cpu().numpy().astype(np.int64)
+
+    env.reset(inject_uniform=U[0])
+    rec = {"obs0": obs_state(), "raw0": raw_state()}
+    lists = {k: [] for k in ("obs", "raw", "theta", "reward", "terminated", "truncated", "was_reset",
+                             "relative_time", "env_change", "delta_change", "gt_change", "gt_delta")}
+    for k in range(K):
+        a = torch.as_tensor(np.asarray(actions[k]).reshape(n_envs))
+        obs, reward, term, trunc, info = env.step(a, inject_uniform=U[k + 1], inject_normal=Z[k + 1])
+        lists["obs"].append(obs_state())
+        lists["raw"].append(raw_state())
+        th = env.theta()
+        cols = []
+        for key in keys:
+            v = th[key].double().cpu().numpy()
+            cols.append(v.T if v.ndim == 2 else v[:, None])
+        lists["theta"].append(np.concatenate(cols, axis=1) if cols else np.zeros((n_envs, 0)))
+        lists["reward"].append(reward.double().cpu().numpy())
+        lists["terminated"].append(term.cpu().numpy())
+        lists["truncated"].append(trunc.cpu().numpy())
+        lists["was_reset"].append(info["was_reset"].cpu().numpy())
+        lists["relative_time"].append(obs["relative_time"].cpu().numpy().astype(np.int64))
+        lists["env_change"].append(np.stack([obs["env_change"][q].cpu().numpy().astype(np.int64) for q in keys], 1))
+        lists["delta_change"].append(np.stack([obs["delta_change"][q].double().cpu().numpy() for q in keys], 1))
+        lists["gt_change"].append(np.stack([info["Ground Truth Env Change"][q].cpu().numpy().astype(np.int64) for q in keys], 1))
+        lists["gt_delta"].append(np.stack([info["Ground Truth Delta Change"][q].double().cpu().numpy() for q in keys], 1))
+    for k2, v in lists.items():
+        rec[k2] = np.stack(v)
+    rec["_bad_dist"] = bool((env.buffers["flags"] & nv.FLAG_BAD_DIST).any().item())
+    del D
+    return rec
+
+
+def compare(ref, got, rtol=FP64_RTOL, atol=FP64_ATOL, float_obs_rtol=None, name=""):
+    """Integer / flag arrays bit-exact; float arrays within (rtol, atol)."""
+    for key in ref:
+        if key.startswith("_") or key not in got:
+            continue
+        a, b = np.asarray(ref[key]), np.asarray(got[key])
+        assert a.shape == b.shape, f"{name}: {key} shape {a.shape} vs {b.shape}"
+        if key in INT_KEYS or a.dtype.kind in "iub":
+            assert np.array_equal(a.astype(np.int64), b.astype(np.int64)), (
+                f"{name}: {key} differs at {np.argwhere(a.astype(np.int64) != b.astype(np.int64))[:5].tolist()}")
+        else:
+            r = rtol if not (float_obs_rtol and key in ("obs", "obs0")) else float_obs_rtol
+            ok = np.isclose(a, b, rtol=r, atol=atol, equal_nan=True)
+            assert ok.all(), (
+                f"{name}: {key} off at {np.argwhere(~ok)[:5].tolist()} "
+                f"ref={a[~ok][:3]} got={b[~ok][:3]} max_abs={np.nanmax(np.abs(a - b))}")
