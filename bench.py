@@ -1,0 +1,396 @@
+#!/usr/bin/env python
+"""bench.py -- NS env-steps/s of the hot path on B200 (BASELINE.json metric), one JSON line.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...   # the reference's CPU path (oracle port)
+
+A *step* is one pass of the hot path over one batch: one kernel launch that advances every
+env of the batch by one NS step (scheduler fire test -> theta advance -> dynamics ->
+termination / truncation -> next-step autoreset).
+
+Workload (config.workload): the C1-shaped NS-CartPole throughput variant of SURVEY 8(d) -- the
+configuration BASELINE.json's target is quoted on: CartPole-v1, masspole IncrementUpdate(k=0.1)
+/ ContinuousScheduler + gravity RandomWalk / PeriodicScheduler(3), change_notification, fp32
+fast mode, native Philox draws, next-step autoreset, 2^24 envs per GPU (1.1 GB of SoA state:
+far larger than the 126 MB L2, so every step streams from HBM).
+
+value   whole-job env-steps/s with actions and state resident in HBM (CUDA events, max over ranks)
+e2e     the same metric through the C-ABI host call nsgym_step_host: actions copied from pinned
+        host memory and observation + reward + flags copied back, every step, inside the timed region
+roofline  algorithmic bytes per launch / CUDA-event launch duration vs MEASURED_PEAKS.json hbm_gbs
+cpu_baseline  the oracle port (the reference's algorithm on the host cores), bounded sample
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "ns_env_steps_per_sec"
+UNIT = "env-steps/s"
+
+WORKLOADS = {
+    # name: (case builder key, env count per GPU, precision)
+    "c1_cartpole": dict(case="c1_cartpole_readme", log2_envs=24, precision="fp32"),
+    "c1_cartpole_fp64": dict(case="c1_cartpole_readme", log2_envs=23, precision="fp64"),
+    "c2_frozenlake8": dict(case="c2_frozenlake8_stepchange", log2_envs=20, precision="fp64"),
+    "c2_frozenlake8_16m": dict(case="c2_frozenlake8_stepchange", log2_envs=24, precision="fp64"),
+    "c3_acrobot": dict(case="c3_acrobot", log2_envs=22, precision="fp32"),
+    "c3_acrobot_fp64": dict(case="c3_acrobot", log2_envs=22, precision="fp64"),
+    "c3_mountaincar": dict(case="c3_mountaincar", log2_envs=22, precision="fp32"),
+    "c3_pendulum": dict(case="c3_pendulum", log2_envs=22, precision="fp32"),
+    "c5_bridge": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64"),
+}
+
+
+# ----------------------------------------------------------------------------------------
+# clocks sampler (B200_PROFILING.md "clocks DURING the timed region")
+# ----------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int, period_ms: int = 50):
+        self.samples = []
+        self.proc = None
+        self.index = index
+        self.period_ms = period_ms
+        self.t_mark = [None, None]
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 f"-lms", str(self.period_ms), "-i", str(self.index)],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except OSError:
+            self.proc = None
+            return
+        threading.Thread(target=self._pump, daemon=True).start()
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.samples.append((time.perf_counter(), line.strip()))
+
+    def mark(self, which):
+        self.t_mark[which] = time.perf_counter()
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        rows = []
+        for ts, line in self.samples:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                rows.append((ts, float(parts[0]), float(parts[1]), parts[3:7]))
+            except ValueError:
+                continue
+        if not rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        t0, t1 = self.t_mark
+        inside = [r for r in rows if t0 is not None and t1 is not None and t0 <= r[0] <= t1]
+        use = inside if len(inside) >= 3 else rows
+        clocks = sorted(r[1] for r in use)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in use for i, v in enumerate(r[3]) if v.lower().startswith("active")})
+        return {"sm_mhz": clocks[len(clocks) // 2], "sm_max_mhz": use[0][2], "reasons": reasons,
+                "samples": len(use), "samples_in_timed_region": len(inside)}
+
+
+# ----------------------------------------------------------------------------------------
+# CPU side: the reference's algorithm (oracle port) on the host cores
+# ----------------------------------------------------------------------------------------
+def make_port_envs(case_name, n):
+    """Module-level (picklable) factory: n oracle-port envs of a tests/cases.py case."""
+    from oracle import harness
+    from tests.cases import CASES
+
+    return harness.port_envs(CASES[case_name], n)
+
+
+def draw_cpu_actions(case_name, rng, n):
+    from tests.cases import CASES
+
+    env_id = CASES[case_name]["env_id"]
+    if "Pendulum" in env_id:
+        return rng.uniform(-2, 2, size=(n, 1))
+    if "MountainCarContinuous" in env_id:
+        return rng.uniform(-1, 1, size=(n, 1))
+    n_act = 2 if "CartPole" in env_id else 3 if ("Acrobot" in env_id or "MountainCar" in env_id) else 4
+    return rng.integers(0, n_act, size=n)
+
+
+def _cpu_make_envs(case_name):
+    import functools
+
+    from tests.cases import CASES
+
+    return functools.partial(make_port_envs, case_name), CASES[case_name]
+
+
+def _cpu_actions(case_name):
+    import functools
+
+    return functools.partial(draw_cpu_actions, case_name)
+
+
+def cpu_baseline(case_name, n_envs_per_proc=64, n_steps=600, n_procs=None):
+    """env-steps/s of the oracle port with one Sync vector loop per host core."""
+    from oracle import vector
+
+    make, case = _cpu_make_envs(case_name)
+    draw = _cpu_actions(case_name)
+    cores = n_procs or os.cpu_count() or 1
+    sync = vector.run_sync(make, n_envs_per_proc, max(n_steps // 4, 50), draw)
+    par = vector.run_parallel(make, n_envs_per_proc, n_steps, draw, cores) if cores > 1 else sync
+    return {
+        "value": par, "unit": UNIT, "cores": cores, "kind": "port",
+        "sync_1core": sync,
+        "sample": (f"oracle port of the reference NS wrappers ({case['env_id']}, {case_name}), next-step-autoreset "
+                   f"vector loop, {n_envs_per_proc} envs x {n_steps} steps per process, {cores} processes"),
+    }
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path.  The reference is
+    pure Python over gymnasium; neither gymnasium nor /root/reference exists on the GPU box, so
+    the timed code is the oracle port (pinned bit-for-bit against the reference in the build
+    container, tests/test_oracle_vs_reference.py), on every host core."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    wl = WORKLOADS[args.workload]
+    per_step = 64
+    make, case = _cpu_make_envs(wl["case"])
+    draw = _cpu_actions(wl["case"])
+    from oracle import vector
+
+    cores = os.cpu_count() or 1
+    steps = max(args.steps, 1)
+    # each bench "step" here = one vector step of `per_step` envs per process; bounded so the
+    # whole run ends within a few minutes
+    n_steps = min(steps * 10, 1500)
+    warm = vector.run_sync(make, per_step, max(args.warmup, 3), draw)
+    del warm
+    t0 = time.perf_counter()
+    value = vector.run_parallel(make, per_step, n_steps, draw, cores) if cores > 1 else \
+        vector.run_sync(make, per_step, n_steps, draw)
+    wall = time.perf_counter() - t0
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / n_steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic",
+        "config": {"workload": args.workload, "case": wl["case"], "envs_per_process": per_step,
+                   "vector_steps": n_steps, "processes": cores},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
+                         "sample": f"{per_step} envs x {n_steps} vector steps per process, {cores} processes"},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------
+# GPU side
+# ----------------------------------------------------------------------------------------
+def build_env(workload, n_envs, rank, seed=0):
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.vector_env import NSVectorEnv
+    from tests.cases import CASES
+
+    wl = WORKLOADS[workload]
+    case = CASES[wl["case"]]
+    env = NSVectorEnv(case["env_id"], case["params"](PS, PU), n_envs, precision=wl["precision"],
+                      autoreset="next_step", seed=seed, env_id_offset=rank * n_envs,
+                      **case.get("wrapper", {}), **case.get("make", {}))
+    return env, case
+
+
+def random_actions(env, gen_seed):
+    import torch
+    from ns_gym_b200.compile import BOX_ACTION, N_ACTIONS
+
+    g = torch.Generator(device=env.device)
+    g.manual_seed(gen_seed)
+    kind = env.program.env_kind
+    if kind in BOX_ACTION:
+        lo, hi = BOX_ACTION[kind]
+        return (torch.rand(env.num_envs, generator=g, device=env.device, dtype=env.real) * (hi - lo) + lo)
+    return torch.randint(0, N_ACTIONS[kind], (env.num_envs,), generator=g, device=env.device, dtype=torch.int32)
+
+
+def time_steps(env, actions, steps, warmup, dist=None):
+    """W untimed + K timed launches, CUDA events on the launching stream; returns seconds."""
+    import torch
+
+    for _ in range(warmup):
+        env.step_raw(actions)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+        torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        env.step_raw(actions)
+    e1.record()
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    return e0.elapsed_time(e1) * 1e-3
+
+
+def run_gpu(args):
+    import torch
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local))
+        dist = dist_mod
+    from ns_gym_b200 import native
+
+    native.load()   # no CUDA library -> loud failure, never a fallback
+    wl = WORKLOADS[args.workload]
+    n_envs = 1 << (args.log2_envs or wl["log2_envs"])
+    env, case = build_env(args.workload, n_envs, rank, seed=args.seed)
+    env.reset(seed=args.seed)
+    actions = random_actions(env, 1234 + rank)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    # ---- device-resident throughput ----
+    launches0 = env.launch_count
+    # long enough for the clock sampler to see the timed region
+    sampler.mark(0)
+    secs = time_steps(env, actions, args.steps, max(args.warmup, 3), dist)
+    sampler.mark(1)
+    launches = env.launch_count - launches0 - max(args.warmup, 3)
+    t = torch.tensor([secs], dtype=torch.float64, device=env.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    secs_max = float(t.item())
+    total_steps = world * n_envs * args.steps
+    value = total_steps / secs_max
+    # ---- roofline for the (only) kernel of the step ----
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    launch_s = secs / args.steps                       # this rank's average launch duration
+    achieved = env.bytes_per_step * n_envs / launch_s / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(args.workload)
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_env_step": env.bytes_per_step,
+                "kernel_us_per_launch": launch_s * 1e6}
+    # ---- end to end through the C-ABI host call ----
+    h_act, h_out = env.make_host_io()
+    h_act.copy_(actions.cpu())
+    e2e_steps = max(min(args.steps, args.e2e_steps), 1)
+    for _ in range(3):
+        env.step_host(h_act, h_out, n_chunks=args.chunks)
+    torch.cuda.synchronize()
+    if dist is not None:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        env.step_host(h_act, h_out, n_chunks=args.chunks)
+    torch.cuda.synchronize()
+    e2e_secs = time.perf_counter() - t0
+    t = torch.tensor([e2e_secs], dtype=torch.float64, device=env.device)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * n_envs * e2e_steps / float(t.item())
+    h2d, d2h = env.host_bytes_per_step(h_act, h_out)
+    # ---- metric reduction over NCCL (the only collective on this path) ----
+    stats = torch.stack([env.buffers["reward"].double().sum(),
+                         ((env.buffers["flags"] & 3) != 0).double().sum(),
+                         torch.tensor(float(n_envs), dtype=torch.float64, device=env.device)])
+    if dist is not None:
+        dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    sampler.stop()
+    if rank == 0:
+        cpu = None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu = cpu_baseline(wl["case"])
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * secs_max / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32" if wl["precision"] == "fp32" else "f64", "data": "synthetic",
+            "config": {
+                "workload": args.workload, "case": wl["case"], "env_id": case["env_id"],
+                "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
+                "autoreset": "next_step", "rng": "philox4x32-10 (native)",
+                "parallelism": f"env-shard x{world}, no data-path collective",
+                "l2_policy": f"working set {env.bytes_per_step * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
+                             "(inputs larger than L2, no flush needed)",
+            },
+            "roofline": roofline,
+            "cpu_baseline": cpu,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "steps": e2e_steps, "chunks": args.chunks,
+                    "api": "nsgym_step_host (C ABI, pinned host buffers, H2D actions + D2H obs/reward/flags/change)"},
+            "gpu_launches": launches,
+            "clocks": sampler.summary(),
+            "batch_stats": {"mean_reward_last_step": float(stats[0] / stats[2]),
+                            "ended_fraction_last_step": float(stats[1] / stats[2])},
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--workload", default="c1_cartpole", choices=sorted(WORKLOADS))
+    ap.add_argument("--log2-envs", type=int, default=None, dest="log2_envs")
+    ap.add_argument("--seed", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=30, dest="e2e_steps")
+    ap.add_argument("--chunks", type=int, default=8)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

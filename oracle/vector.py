@@ -187,11 +187,11 @@ def run_sync(make_envs, n_envs, n_steps, action_fn, seed=0):
 
 def run_parallel(make_envs, n_envs_per_proc, n_steps, action_fn, n_procs, seed=0):
     """env-steps/s with one Sync loop per process (the AsyncVectorEnv-style arrangement:
-    envs partitioned over worker processes).  Throughput = total steps / slowest worker."""
+    envs partitioned over worker processes).  Each worker times its own stepping loop (env
+    construction and process start-up excluded, as for the GPU arm); throughput = total
+    steps / slowest worker."""
     ctx = mp.get_context("fork")
     with ctx.Pool(n_procs) as pool:
-        t0 = time.perf_counter()
-        pool.map(_worker, [(make_envs, n_envs_per_proc, n_steps, action_fn, seed + i)
-                           for i in range(n_procs)])
-        wall = time.perf_counter() - t0
-    return n_procs * n_envs_per_proc * n_steps / wall
+        times = pool.map(_worker, [(make_envs, n_envs_per_proc, n_steps, action_fn, seed + i)
+                                   for i in range(n_procs)])
+    return n_procs * n_envs_per_proc * n_steps / max(times)

@@ -96,7 +96,8 @@ def compare(ref, got, rtol=FP64_RTOL, atol=FP64_ATOL, float_obs_rtol=None, name=
             assert np.array_equal(a.astype(np.int64), b.astype(np.int64)), (
                 f"{name}: {key} differs at {np.argwhere(a.astype(np.int64) != b.astype(np.int64))[:5].tolist()}")
         else:
-            r = rtol if not (float_obs_rtol and key in ("obs", "obs0")) else float_obs_rtol
+            # observations and rewards leave the kernel as float32 (gymnasium's obs dtype)
+            r = rtol if not (float_obs_rtol and key in ("obs", "obs0", "reward")) else float_obs_rtol
             ok = np.isclose(a, b, rtol=r, atol=atol, equal_nan=True)
             assert ok.all(), (
                 f"{name}: {key} off at {np.argwhere(~ok)[:5].tolist()} "
