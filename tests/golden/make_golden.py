@@ -1,0 +1,43 @@
+"""Generate golden vectors from the REAL reference (run in the build container only).
+
+    python tests/golden/make_golden.py
+
+For every case of tests/cases.py this imports /root/reference/ns_gym verbatim on top of the
+restated gymnasium shim (oracle/ref_loader.py), injects pre-drawn uniform / normal tables
+(oracle/streams.py), drives N envs through the next-step-autoreset vector loop and stores
+the inputs (actions, tables) and every output (observations, raw fp64 states, theta, rewards,
+flags, change masks, deltas) in tests/golden/<case>.npz.  The fixtures travel to the GPU box,
+where /root/reference does not exist.
+"""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+sys.path.insert(0, ROOT)
+
+from oracle import harness, ref_loader, vector  # noqa: E402
+from tests.cases import CASES  # noqa: E402
+from tests.parity_util import n_slots_of  # noqa: E402
+
+N_ENVS = 4
+SEED = 101
+
+
+def main():
+    assert ref_loader.available(), "the reference tree is needed to (re)generate golden vectors"
+    out_dir = os.path.dirname(os.path.abspath(__file__))
+    for name, case in sorted(CASES.items()):
+        K = case["steps"]
+        actions = harness.draw_actions(case, SEED + 1, K, N_ENVS)
+        clock, per_env, u, z = harness.make_streams(SEED, N_ENVS, K + 1, n_slots_of(case))
+        envs = harness.reference_envs(case, N_ENVS, per_env)
+        tr = vector.trace(vector.SyncVector(envs, per_env, clock), actions)
+        tr = {k: (v.astype(np.int8) if v.dtype == bool else v) for k, v in tr.items()}
+        np.savez_compressed(os.path.join(out_dir, f"{name}.npz"), actions=actions, uniforms=u, normals=z, **tr)
+        print(f"{name}: K={K} N={N_ENVS} ended={int(tr['terminated'].sum() + tr['truncated'].sum())}")
+
+
+if __name__ == "__main__":
+    main()

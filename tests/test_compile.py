@@ -1,0 +1,133 @@
+"""CPU: host logic of the compiler (tunable_params -> opcode table)."""
+import numpy as np
+import pytest
+
+import ns_gym_b200.schedulers as S
+import ns_gym_b200.update_functions as U
+from ns_gym_b200 import native as nv
+from ns_gym_b200.compile import CompileError, compile_program
+from tests.cases import CASES
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_every_case_compiles(name):
+    c = CASES[name]
+    p = compile_program(c["env_id"], c["params"](S, U), 16, precision="fp64", **c["wrapper"], **c["make"])
+    assert p.spec.n_slots == len(p.keys) == len(c["params"](S, U))
+    assert [p.spec.slots[j].theta_index for j in range(p.spec.n_slots)] == sorted(
+        {p.spec.slots[j].theta_index for j in range(p.spec.n_slots)}, key=lambda i: [
+            p.spec.slots[j].theta_index for j in range(p.spec.n_slots)].index(i))
+
+
+def test_slot_order_is_dict_order():
+    tp = {"length": U.NoUpdate(S.ContinuousScheduler()), "gravity": U.NoUpdate(S.ContinuousScheduler())}
+    p = compile_program("CartPole-v1", tp, 4)
+    assert p.keys == ["length", "gravity"]
+    assert [p.spec.slots[j].theta_index for j in range(2)] == [5, 0]
+
+
+def test_scheduler_lowering():
+    tp = {"gravity": U.IncrementUpdate(S.PeriodicScheduler(3, start=2.5, end=9.9), k=1.0)}
+    s = compile_program("CartPole-v1", tp, 4).spec.slots[0]
+    assert (s.sched_op, s.si[0], s.start, s.end) == (nv.SCHED_PERIODIC, 3, 3, 9)
+    tp = {"gravity": U.IncrementUpdate(S.ContinuousScheduler(), k=1.0)}
+    s = compile_program("CartPole-v1", tp, 4).spec.slots[0]
+    assert (s.start, s.end) == (0, nv.INT32_MAX)
+    tp = {"gravity": U.IncrementUpdate(S.DiscreteScheduler({1, 33}), k=1.0)}
+    p = compile_program("CartPole-v1", tp, 4)
+    s = p.spec.slots[0]
+    assert s.sched_op == nv.SCHED_BITMAP and s.si[1] == 34
+    words = [p.spec.bitmap[i] for i in range(p.spec.n_bitmap_words)]
+    assert words == [2, 2]
+    tp = {"gravity": U.IncrementUpdate(S.CustomScheduler(lambda t: t in (0, 499, 500)), k=1.0)}
+    p = compile_program("CartPole-v1", tp, 4)                        # horizon = TimeLimit 500
+    assert p.spec.slots[0].si[1] == 501
+    tp = {"gravity": U.IncrementUpdate(S.MemorylessScheduler(p=0.3, seed=3), k=1.0)}
+    s = compile_program("CartPole-v1", tp, 4).spec.slots[0]
+    assert s.sched_op == nv.SCHED_MEMORYLESS and s.istate_plane == 0
+    assert s.istate_init == int(np.random.default_rng(3).geometric(p=0.3, size=(1,))[0])
+
+
+def test_update_lowering_coefficients():
+    tp = {"gravity": U.DecrementUpdate(S.ContinuousScheduler(), k=0.25),
+          "length": U.LinearInterpolation(S.ContinuousScheduler(), 0.5, 0.8, T=25),
+          "tau": U.SigmoidTransition(S.ContinuousScheduler(), a=0.02, b=0.03, k=0.5, t0=10)}
+    sp = compile_program("CartPole-v1", tp, 4).spec
+    assert (sp.slots[0].upd_op, sp.slots[0].uf[0]) == (nv.UPD_ADD, -0.25)
+    assert list(sp.slots[1].uf)[:3] == [0.5, 0.8 - 0.5, 25.0]
+    assert list(sp.slots[2].uf)[:4] == [0.02, 0.03 - 0.02, 0.5, 10.0]
+    assert sp.slots[0].constraint == nv.CONS_REJECT_LT0 and sp.slots[1].constraint == nv.CONS_REJECT_LE0
+    assert sp.slots[2].constraint == nv.CONS_NONE
+
+
+def test_acrobot_partner_slots():
+    tp = {"LINK_COM_POS_1": U.NoUpdate(S.ContinuousScheduler()), "LINK_LENGTH_1": U.NoUpdate(S.ContinuousScheduler()),
+          "LINK_COM_POS_2": U.NoUpdate(S.ContinuousScheduler())}
+    sp = compile_program("Acrobot-v1", tp, 4).spec
+    assert (sp.slots[0].constraint, sp.slots[0].partner_slot, sp.slots[0].partner_index) == (nv.CONS_ACRO_COM, 1, 1)
+    assert (sp.slots[1].constraint, sp.slots[1].partner_slot, sp.slots[1].partner_index) == (nv.CONS_ACRO_LENGTH1, 0, 5)
+    assert (sp.slots[2].partner_slot, sp.slots[2].partner_index) == (-1, 2)
+
+
+def test_reference_assertions_are_kept():
+    with pytest.raises(AssertionError):                               # base.py:257-261
+        compile_program("CartPole-v1", {"not_a_param": U.NoUpdate(S.ContinuousScheduler())}, 4)
+    with pytest.raises(AssertionError):                               # toy_text.py:329-334
+        compile_program("FrozenLake-v1", {"P": U.DistributionNoUpdate(S.ContinuousScheduler())}, 4,
+                        initial_prob_dist=[0.5, 0.2, 0.2])
+    with pytest.raises(AssertionError):                               # base.py:114-119
+        U.IncrementUpdate("not_a_scheduler", k=1.0)
+    with pytest.raises(AssertionError):                               # schedulers.py:66-71
+        S.DiscreteScheduler({1, 50}, start=0, end=10)
+
+
+def test_rejections():
+    fn = U.RandomWalk(S.ContinuousScheduler())
+    with pytest.raises(CompileError):
+        compile_program("CartPole-v1", {"gravity": fn, "length": fn}, 4)   # shared stateful object (S13)
+    with pytest.raises(CompileError):
+        compile_program("FrozenLake-v1", {"P": U.RandomCategorical(S.ContinuousScheduler())}, 4)
+    with pytest.raises(CompileError):
+        compile_program("CartPole-v1", {"gravity": U.UniformDrift(S.ContinuousScheduler(), 0.1)}, 4)
+    with pytest.raises(CompileError):
+        compile_program("Nope-v0", {}, 4)
+    # stateless objects may be shared (the reference's own fixtures do it: test_step_reset.py:36-44)
+    inc = U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)
+    assert compile_program("CartPole-v1", {"masspole": inc, "gravity": inc}, 4).spec.n_slots == 2
+
+
+def test_gridworld_maps():
+    p = compile_program("FrozenLake-v1", {"P": U.DistributionNoUpdate(S.ContinuousScheduler())}, 4, map_name="8x8")
+    sp = p.spec
+    assert (sp.nrow, sp.ncol, sp.start_cell, sp.n_dist) == (8, 8, 0, 3)
+    assert sp.goal_mask == 1 << 63 and bin(sp.hole_mask).count("1") == 10
+    p = compile_program("ns_gym/Bridge-v0", {"P_left": U.DistributionNoUpdate(S.ContinuousScheduler())}, 4,
+                        initial_prob_dist=([0.9, 0.05, 0.05], [1, 0, 0]))
+    sp = p.spec
+    assert sp.split_mode == 1 and sp.start_cell == 20 and (sp.nrow, sp.ncol) == (5, 8)
+    assert list(sp.theta_init[1])[:3] == [0.9, 0.05, 0.05] and list(sp.theta_init[2])[:3] == [1, 0, 0]
+    assert bin(sp.goal_mask).count("1") == 2
+    p = compile_program("CliffWalking-v1", {"P": U.DistributionNoUpdate(S.ContinuousScheduler())}, 4)
+    assert p.spec.start_cell == 36 and p.spec.n_dist == 4 and p.spec.max_episode_steps == 0
+
+
+def test_reference_objects_compile_too():
+    """Duck typing: dictionaries built from the reference's own classes compile unchanged."""
+    from oracle import ref_loader
+
+    if not ref_loader.available():
+        pytest.skip("reference tree not present")
+    ref_loader.load()
+    import ns_gym.schedulers as RS
+    import ns_gym.update_functions as RU
+
+    for name in ("c1_cartpole_readme", "cartpole_all_params", "c5_bridge_split", "cartpole_stochastic_scheds"):
+        c = CASES[name]
+        a = compile_program(c["env_id"], c["params"](RS, RU), 8, **c["wrapper"], **c["make"]).spec
+        b = compile_program(c["env_id"], c["params"](S, U), 8, **c["wrapper"], **c["make"]).spec
+        for j in range(a.n_slots):
+            sa, sb = a.slots[j], b.slots[j]
+            assert (sa.sched_op, sa.upd_op, sa.theta_index, sa.start, sa.end) == (
+                sb.sched_op, sb.upd_op, sb.theta_index, sb.start, sb.end)
+            assert list(sa.uf) == list(sb.uf) and list(sa.sf) == list(sb.sf)
+            assert list(sa.si) == list(sb.si) and sa.istate_init == sb.istate_init

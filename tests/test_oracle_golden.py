@@ -1,0 +1,34 @@
+"""CPU: the oracle port reproduces the golden vectors generated from the REAL reference
+(tests/golden/make_golden.py) bit for bit.  Runs everywhere, including the GPU box where the
+reference tree is absent."""
+import glob
+import os
+
+import numpy as np
+import pytest
+
+from oracle import harness, streams, vector
+from tests.cases import CASES
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "*.npz")))
+
+
+def test_every_case_has_a_golden_file():
+    assert set(NAMES) == set(CASES)
+
+
+@pytest.mark.parametrize("name", NAMES)
+def test_port_matches_golden(name):
+    g = np.load(os.path.join(GOLDEN, f"{name}.npz"))
+    case = CASES[name]
+    u, z, actions = g["uniforms"], g["normals"], g["actions"]
+    n = u.shape[2]
+    clock = streams.Clock()
+    per_env = [streams.EnvStreams(u[:, :, i], z[:, :, i], clock) for i in range(n)]
+    envs = harness.port_envs(case, n, per_env)
+    tr = vector.trace(vector.SyncVector(envs, per_env, clock), actions)
+    for key, got in tr.items():
+        want = g[key]
+        assert np.array_equal(np.asarray(got).astype(want.dtype) if want.dtype.kind in "iu" else got, want,
+                              equal_nan=got.dtype.kind == "f"), f"{name}: {key} differs from golden"
