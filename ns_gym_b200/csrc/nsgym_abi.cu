@@ -176,6 +176,22 @@ int nsgym_create(const NsgymSpec* spec, NsgymHandle** out) {
   NsgymHandle* h = new (std::nothrow) NsgymHandle();
   if (!h) return fail(-3, "out of host memory");
   h->spec = *spec;
+  // fast_mod magic (device: nsgym_device.cuh): exact while t * d < 2^32 over the reachable t
+  {
+    const uint64_t t_max = (spec->autoreset == NSGYM_AUTORESET_NEXT_STEP && spec->max_episode_steps > 0)
+                               ? uint64_t(spec->max_episode_steps) + 1 : (1ull << 28);
+    for (int j = 0; j < spec->n_slots; ++j) {
+      NsgymSlot& sl = h->spec.slots[j];
+      int d = 0;
+      if (sl.sched_op == NSGYM_SCHED_PERIODIC) d = sl.si[0];
+      if (sl.sched_op == NSGYM_SCHED_BURST) d = sl.si[1];
+      if (d >= 2 || sl.sched_op == NSGYM_SCHED_PERIODIC || sl.sched_op == NSGYM_SCHED_BURST) {
+        sl.si[2] = 0;
+        if (d >= 2 && t_max * uint64_t(d) < (1ull << 32))
+          sl.si[2] = int32_t(uint32_t(((1ull << 32) + uint64_t(d) - 1) / uint64_t(d)));
+      }
+    }
+  }
   int planes = 0;
   for (int j = 0; j < spec->n_slots; ++j)
     if (spec->slots[j].istate_plane >= 0) planes = planes > spec->slots[j].istate_plane + 1 ? planes : spec->slots[j].istate_plane + 1;

@@ -15,6 +15,15 @@ static ProgramT<R, MAXP> build_program(const NsgymSpec& spec, const DevicePools&
   P.max_steps = spec.max_episode_steps;
   P.autoreset = spec.autoreset;
   P.persistent = spec.persistent_params;
+  // block 0 of the Philox stream is consumed by next-step autoreset (initial-state draws), by the
+  // normals of slots 0 / 1 and by the gridworld slip draw: compute it once, before any branch
+  bool stochastic01 = false;
+  for (int j = 0; j < spec.n_slots && j < 2; ++j) {
+    const int op = spec.slots[j].upd_op;
+    stochastic01 |= (op == NSGYM_UPD_RW || op == NSGYM_UPD_OU || op == NSGYM_UPD_BRW);
+  }
+  P.rng_prefetch = (spec.autoreset == NSGYM_AUTORESET_NEXT_STEP && !is_grid_kind(spec.env_kind)) || stochastic01 ||
+                   is_grid_kind(spec.env_kind);
   for (int i = 0; i < NSGYM_MAX_THETA; ++i) P.theta_default[i] = R(spec.theta_init[i][0]);
   for (int j = 0; j < spec.n_slots && j < MAXP; ++j) {
     const NsgymSlot& a = spec.slots[j];
