@@ -86,6 +86,7 @@ int validate(const NsgymSpec* s) {
     return fail(-1, "ABI version mismatch: caller %d, library %d", s->abi_version, NSGYM_ABI_VERSION);
   if (s->env_kind < 0 || s->env_kind >= NSGYM_ENV_COUNT) return fail(-1, "unknown env_kind %d", s->env_kind);
   if (s->n_envs <= 0) return fail(-1, "n_envs must be positive");
+  if (s->n_envs > (int64_t(1) << 28)) return fail(-1, "n_envs per handle is limited to 2^28 (32-bit plane indexing)");
   if (s->n_slots < 0 || s->n_slots > NSGYM_MAX_SLOTS) return fail(-1, "n_slots %d out of range", s->n_slots);
   const KindInfo& k = kKinds[s->env_kind];
   if (s->n_slots > k.n_theta) return fail(-1, "%d slots > %d tunable parameters of this env", s->n_slots, k.n_theta);
