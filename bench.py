@@ -48,6 +48,14 @@ WORKLOADS = {
     "c3_mountaincar": dict(case="c3_mountaincar", log2_envs=22, precision="fp32"),
     "c3_pendulum": dict(case="c3_pendulum", log2_envs=22, precision="fp32"),
     "c5_bridge": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64"),
+    # K-step fused rollouts (state + theta in registers, device-side uniform-random policy)
+    "c5_bridge_rollout8": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64", rollout_k=8),
+    "c5_bridge_rollout32": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64", rollout_k=32),
+    "c5_bridge_rollout100": dict(case="c5_bridge_uniform", log2_envs=26, precision="fp64", rollout_k=100),
+    "c5_bridge_split_rollout32": dict(case="c5_bridge_split", log2_envs=24, precision="fp64", rollout_k=32),
+    "c1_cartpole_rollout32": dict(case="c1_cartpole_readme", log2_envs=24, precision="fp32", rollout_k=32),
+    "c3_acrobot_rollout32": dict(case="c3_acrobot", log2_envs=22, precision="fp32", rollout_k=32),
+    "c3_acrobot_fp64_rollout32": dict(case="c3_acrobot", log2_envs=22, precision="fp64", rollout_k=32),
 }
 
 
@@ -238,12 +246,27 @@ def random_actions(env, gen_seed):
     return torch.randint(0, N_ACTIONS[kind], (env.num_envs,), generator=g, device=env.device, dtype=torch.int32)
 
 
-def time_steps(env, actions, steps, warmup, dist=None):
+def time_steps(env, actions, steps, warmup, dist=None, rollout_k=0):
     """W untimed + K timed launches, CUDA events on the launching stream; returns seconds."""
     import torch
 
+    if rollout_k:
+        ret = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
+        length = torch.zeros(env.num_envs, dtype=torch.int32, device=env.device)
+
+        def launch():
+            env.rollout(rollout_k, 1.0, ret, length)
+    else:
+        def launch():
+            env.step_raw(actions)
+    return _time_launches(launch, steps, warmup, dist)
+
+
+def _time_launches(launch, steps, warmup, dist=None):
+    import torch
+
     for _ in range(warmup):
-        env.step_raw(actions)
+        launch()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
@@ -251,7 +274,7 @@ def time_steps(env, actions, steps, warmup, dist=None):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
-        env.step_raw(actions)
+        launch()
     e1.record()
     torch.cuda.synchronize()
     if dist is not None:
@@ -287,14 +310,16 @@ def run_gpu(args):
     launches0 = env.launch_count
     # long enough for the clock sampler to see the timed region
     sampler.mark(0)
-    secs = time_steps(env, actions, args.steps, max(args.warmup, 3), dist)
+    rollout_k = int(wl.get("rollout_k", 0))
+    per_launch = max(rollout_k, 1)                     # env-steps each env advances per launch
+    secs = time_steps(env, actions, args.steps, max(args.warmup, 3), dist, rollout_k)
     sampler.mark(1)
     launches = env.launch_count - launches0 - max(args.warmup, 3)
     t = torch.tensor([secs], dtype=torch.float64, device=env.device)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs_max = float(t.item())
-    total_steps = world * n_envs * args.steps
+    total_steps = world * n_envs * args.steps * per_launch
     value = total_steps / secs_max
     # ---- roofline for the (only) kernel of the step ----
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
@@ -304,7 +329,12 @@ def run_gpu(args):
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
     launch_s = secs / args.steps                       # this rank's average launch duration
-    achieved = env.bytes_per_step * n_envs / launch_s / 1e9
+    bytes_per_launch_env = env.bytes_per_step
+    if rollout_k:
+        # K fused steps move state / theta / t once per launch and write the return + length
+        # accumulators: (2 S w + 2 P w + 8) + 12 per env per launch
+        bytes_per_launch_env = env.bytes_per_step - (env.buffers["action"].element_size() + 4 + 1 + 1) + 12 + 6
+    achieved = bytes_per_launch_env * n_envs / launch_s / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(tpath):
@@ -312,8 +342,11 @@ def run_gpu(args):
             traffic = json.load(f).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_env_step": env.bytes_per_step,
+                "algorithmic_bytes_per_env_step": bytes_per_launch_env / per_launch,
                 "kernel_us_per_launch": launch_s * 1e6}
+    if rollout_k:
+        roofline["note"] = (f"fused {rollout_k}-step rollout: bytes are amortised over K steps, the kernel is "
+                            "FP32/FP64-pipe + issue bound, not HBM bound (see profiles/)")
     # ---- end to end through the C-ABI host call ----
     h_act, h_out = env.make_host_io()
     h_act.copy_(actions.cpu())
@@ -352,7 +385,7 @@ def run_gpu(args):
             "config": {
                 "workload": args.workload, "case": wl["case"], "env_id": case["env_id"],
                 "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
-                "autoreset": "next_step", "rng": "philox4x32-10 (native)",
+                "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k,
                 "parallelism": f"env-shard x{world}, no data-path collective",
                 "l2_policy": f"working set {env.bytes_per_step * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",

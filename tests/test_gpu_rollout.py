@@ -1,0 +1,107 @@
+"""GPU: the K-step fused rollout kernel equals K single-step launches fed with the same actions.
+
+The rollout draws its actions from Philox block 13 of each env-step; tests/philox_np.py restates
+the stream in NumPy, so the single-step path can be driven with identical actions.  Both paths
+then run the same device arithmetic with the same native Philox draws (same seed, same step
+indices, same global env ids): states, theta, t, returns and lengths must agree bit for bit."""
+import numpy as np
+import pytest
+
+from tests import philox_np
+from tests.cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+ROLLOUT_CASES = [("c1_cartpole_readme", "cartpole", "fp32"), ("c1_cartpole_readme", "cartpole", "fp64"),
+                 ("c3_acrobot", "acrobot", "fp32"), ("c3_mountaincar", "mountaincar", "fp64"),
+                 ("c3_pendulum", "pendulum", "fp32"), ("c5_bridge_uniform", "grid", "fp64"),
+                 ("c5_bridge_split", "grid", "fp64"), ("c2_frozenlake8_drift", "grid", "fp64"),
+                 ("cliff_terminal", "grid", "fp64")]
+
+
+def _make(case, n, precision, seed, offset=0):
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.vector_env import NSVectorEnv
+
+    env = NSVectorEnv(case["env_id"], case["params"](PS, PU), n, precision=precision, seed=seed,
+                      env_id_offset=offset, **case.get("wrapper", {}), **case.get("make", {}))
+    env.reset(seed=seed)
+    return env
+
+
+@pytest.mark.parametrize("name,kind,precision", ROLLOUT_CASES)
+def test_rollout_equals_single_steps(name, kind, precision):
+    import torch
+
+    case, n, K, seed, offset = CASES[name], 4096, 37, 1234, 10_000
+    a = _make(case, n, precision, seed, offset)
+    b = _make(case, n, precision, seed, offset)
+    step0 = int(a.lib.nsgym_step_index(a._h))
+    assert step0 == int(b.lib.nsgym_step_index(b._h))
+    ret, length = a.rollout(K, gamma=1.0)
+    gids = np.arange(offset, offset + n, dtype=np.uint64)
+    acc = torch.zeros(n, dtype=torch.float32, device=b.device)
+    steps_alive = torch.zeros(n, dtype=torch.int32, device=b.device)
+    first = torch.ones(n, dtype=torch.bool, device=b.device)
+    for k in range(K):
+        act = philox_np.policy_actions(kind, gids, step0 + k, seed)
+        obs, r, term, trunc, info = b.step(torch.as_tensor(act))
+        was_reset = info["was_reset"]
+        first &= ~was_reset
+        steps_alive += (first & ~was_reset).int()
+        acc += r
+    torch.cuda.synchronize()
+    for key in ("state", "theta", "t", "istate"):
+        x, y = a.buffers[key], b.buffers[key]
+        if x is not None:
+            assert torch.equal(x, y), f"{name}: {key} differs after the rollout"
+    assert torch.equal(ret, acc)
+    assert torch.equal(length, steps_alive)
+    assert int(a.lib.nsgym_step_index(a._h)) == step0 + K
+
+
+def test_rollout_is_shard_invariant():
+    """Global-id Philox keys: two half-size shards reproduce one full-size batch."""
+    import torch
+
+    case, n, K, seed = CASES["c5_bridge_uniform"], 2048, 25, 7
+    full = _make(case, n, "fp64", seed, 0)
+    lo = _make(case, n // 2, "fp64", seed, 0)
+    hi = _make(case, n // 2, "fp64", seed, n // 2)
+    rf, lf = full.rollout(K)
+    r0, l0 = lo.rollout(K)
+    r1, l1 = hi.rollout(K)
+    assert torch.equal(rf, torch.cat([r0, r1])) and torch.equal(lf, torch.cat([l0, l1]))
+    assert torch.equal(full.buffers["state"], torch.cat([lo.buffers["state"], hi.buffers["state"]]))
+
+
+def test_frozen_planning_env_keeps_theta():
+    """is_sim_env with in_sim_change False: theta frozen, t still advances (classic_control.py:70-75)."""
+    import torch
+
+    env = _make(CASES["c1_cartpole_readme"], 512, "fp64", 3)
+    env.is_sim_env = True
+    th0 = env.buffers["theta"].clone()
+    t0 = env.relative_time().clone()
+    a = torch.zeros(512, dtype=torch.int32, device=env.device)
+    for _ in range(3):
+        obs, r, term, trunc, info = env.step(a)
+    assert torch.equal(env.buffers["theta"], th0)
+    assert torch.equal(env.relative_time(), t0 + 3)
+    assert all(int(v.sum()) == 0 for v in obs["env_change"].values())
+    assert all(int(v.sum()) == 0 for v in info["Ground Truth Env Change"].values())
+
+
+def test_device_philox_matches_numpy_restatement():
+    """CartPole fp32 reset state = -0.05 + 0.1 * (word >> 8) * 2^-24 for the four words of block 0."""
+    import torch
+
+    n, seed, offset = 1000, 99, 123456789012
+    env = _make(CASES["c1_cartpole_readme"], n, "fp32", seed, offset)
+    step_of_reset = int(env.lib.nsgym_step_index(env._h)) - 1
+    words = philox_np.block(np.arange(offset, offset + n, dtype=np.uint64), step_of_reset, 0, seed)
+    want = np.stack([np.float32(-0.05) + (np.float32(0.05) - np.float32(-0.05)) *
+                     ((w >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)) for w in words], 1)
+    got = env.buffers["state"].cpu().numpy()
+    np.testing.assert_allclose(got, want, rtol=0, atol=1e-8)

@@ -102,3 +102,14 @@ def test_bridge_transitions_known_answers():
     assert (s, r, done) == (12, 0, False)
     s, r, done, _, _ = b.step(3)                                   # (0, 4) is H
     assert (s, r, done) == (4, -1, True)
+
+
+def test_numpy_philox_known_answer_vectors():
+    """Random123 kat_vectors for philox4x32_10 (tests/philox_np.py restates the device stream)."""
+    from tests import philox_np as p
+
+    z = np.uint32([0])
+    assert [int(x[0]) for x in p.philox4x32_10(z, z, z, z, 0)] == [0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8]
+    f = np.uint32([0xffffffff])
+    assert [int(x[0]) for x in p.philox4x32_10(f, f, f, f, 0xffffffffffffffff)] == [
+        0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd]
