@@ -112,6 +112,12 @@ int validate(const NsgymSpec* s) {
     if (sl.sched_op < 0 || sl.sched_op >= NSGYM_SCHED_COUNT) return fail(-1, "slot %d: bad sched_op", j);
     const bool dist_op = sl.upd_op >= NSGYM_UPD_D_NOP;
     if (dist_op != grid) return fail(-1, "slot %d: update opcode %d does not fit this env kind", j, sl.upd_op);
+    // the Acrobot cross-checks are wired to fixed partners (classic_control.py:241-265, :307-357)
+    if (sl.constraint == NSGYM_CONS_ACRO_LENGTH1 && !(s->env_kind == NSGYM_ENV_ACROBOT && sl.theta_index == 1))
+      return fail(-1, "slot %d: NSGYM_CONS_ACRO_LENGTH1 belongs to Acrobot LINK_LENGTH_1", j);
+    if (sl.constraint == NSGYM_CONS_ACRO_COM &&
+        !(s->env_kind == NSGYM_ENV_ACROBOT && (sl.theta_index == 5 || sl.theta_index == 6)))
+      return fail(-1, "slot %d: NSGYM_CONS_ACRO_COM belongs to Acrobot LINK_COM_POS_1 / LINK_COM_POS_2", j);
     if (sl.sched_op == NSGYM_SCHED_PERIODIC && sl.si[0] <= 0) return fail(-1, "slot %d: period must be > 0", j);
     if (sl.sched_op == NSGYM_SCHED_BURST && sl.si[1] <= 0) return fail(-1, "slot %d: burst cycle must be > 0", j);
     if (sl.sched_op == NSGYM_SCHED_BITMAP &&

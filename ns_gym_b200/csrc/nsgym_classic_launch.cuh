@@ -3,6 +3,7 @@
 #pragma once
 #include <limits>
 #include <type_traits>
+#include <utility>
 
 #include "nsgym_device.cuh"
 #include "nsgym_host.h"
@@ -18,51 +19,118 @@ template <typename R> struct TrueMin;
 template <> struct TrueMin<float> { static constexpr float value = 1.401298464324817e-45f; };
 template <> struct TrueMin<double> { static constexpr double value = 4.9406564584124654e-324; };
 
-template <typename R, int MAXP>
-static ProgramT<R, MAXP> build_program(const NsgymSpec& spec, const DevicePools& pools) {
-  ProgramT<R, MAXP> P{};
-  P.n_slots = spec.n_slots < MAXP ? spec.n_slots : MAXP;
+// Lower one ABI slot to the kernel's form (SlotT): fast / slow class, range gate in unsigned
+// form, multiply-high modulo, affine coefficients, constraint threshold.
+template <typename R>
+static SlotT<R> lower_slot(const NsgymSlot& a, int lane) {
+  SlotT<R> b{};
+  b.lane = lane;
+  b.sched_op = a.sched_op; b.upd_op = a.upd_op; b.constraint = a.constraint;
+  b.istate_plane = a.istate_plane; b.istate_init = a.istate_init;
+  for (int k = 0; k < 4; ++k) { b.si[k] = a.si[k]; b.ui[k] = a.ui[k]; }
+  b.sf[0] = a.sf[0]; b.sf[1] = a.sf[1];
+  for (int k = 0; k < 6; ++k) b.uf[k] = R(a.uf[k]);
+  // ---- range gate: start <= t <= end  <=>  unsigned(t - start) <= unsigned(end - start) ----
+  const int32_t t_cap = (1 << 28);                       // t never exceeds T_TIME_MASK
+  int32_t lo = a.start < 0 ? 0 : a.start, hi = a.end > t_cap ? t_cap : a.end;
+  if (lo > t_cap || hi < lo) { b.start = INT32_MAX; b.span = 0; }   // never in range
+  else { b.start = lo; b.span = hi - lo; }
+  // ---- scheduler: fast class = in range && (t mod d) < on ----
+  b.mod_d = 0; b.mod_magic = 0; b.mod_on = INT32_MAX;    // Continuous: t - 0 < INT_MAX
+  switch (a.sched_op) {
+    case NSGYM_SCHED_CONTINUOUS: break;
+    case NSGYM_SCHED_PERIODIC:
+      if (a.si[0] == 1) break;                           // t % 1 == 0 always
+      if (a.si[2]) { b.mod_d = a.si[0]; b.mod_magic = a.si[2]; b.mod_on = 1; }
+      else b.flags |= SF_SLOW_SCHED;
+      break;
+    case NSGYM_SCHED_BURST:
+      if (a.si[1] == 1) { b.mod_on = a.si[0] > 0 ? INT32_MAX : 0; break; }   // (t % 1) < on
+      if (a.si[2]) { b.mod_d = a.si[1]; b.mod_magic = a.si[2]; b.mod_on = a.si[0]; }
+      else b.flags |= SF_SLOW_SCHED;
+      break;
+    default: b.flags |= SF_SLOW_SCHED; break;
+  }
+  // ---- update: fast class = ((A y + B) + noise) + C t ----
+  double A = 1.0, B = 0.0, Ct = 0.0;
+  switch (a.upd_op) {
+    case NSGYM_UPD_NOP: break;
+    case NSGYM_UPD_ADD: B = a.uf[0]; break;
+    case NSGYM_UPD_ADD_T: Ct = a.uf[0]; break;
+    case NSGYM_UPD_MUL: A = a.uf[0]; break;
+    case NSGYM_UPD_RW: B = a.uf[0]; Ct = a.uf[3]; b.flags |= SF_NORMAL; break;
+    default: b.flags |= SF_SLOW_UPD; break;
+  }
+  b.fa[0] = R(A); b.fa[1] = R(B); b.fa[2] = R(Ct);
+  b.mu = R(a.uf[1]); b.sigma = R(a.uf[2]);
+  // `v <= 0` -> v <= 0;  `v < 0` -> v <= -(smallest subnormal);  none -> v <= -inf (never)
+  if (a.constraint == NSGYM_CONS_REJECT_LE0) b.reject_le = R(0);
+  else if (a.constraint == NSGYM_CONS_REJECT_LT0) b.reject_le = -TrueMin<R>::value;
+  else b.reject_le = -std::numeric_limits<R>::infinity();
+  return b;
+}
+
+inline bool slot_draws_block0(const NsgymSlot& a, int lane) {
+  return lane < 2 && (a.upd_op == NSGYM_UPD_RW || a.upd_op == NSGYM_UPD_OU || a.upd_op == NSGYM_UPD_BRW);
+}
+
+template <typename R, int NP>
+static void program_common(ProgramT<R, NP>& P, const NsgymSpec& spec, const DevicePools& pools) {
   P.max_steps = spec.max_episode_steps;
   P.autoreset = spec.autoreset;
   P.persistent = spec.persistent_params;
   for (int i = 0; i < NSGYM_MAX_THETA; ++i) P.theta_default[i] = R(spec.theta_init[i][0]);
-  bool stochastic01 = false;
-  for (int j = 0; j < P.n_slots; ++j) {
+  P.pool_f = pools.pool_f; P.pool_i = pools.pool_i; P.bitmap = pools.bitmap;
+}
+
+// classic control: slots in tunable_params order, NP = spec.n_slots exactly
+template <typename R, int NP>
+static ProgramT<R, NP> build_program(const NsgymSpec& spec, const DevicePools& pools) {
+  ProgramT<R, NP> P{};
+  program_common(P, spec, pools);
+  for (int q = 0; q < NSGYM_MAX_THETA; ++q) P.base[q] = P.theta_default[q];
+  for (int j = 0; j < NP; ++j) {
     const NsgymSlot& a = spec.slots[j];
     SlotT<R>& b = P.slot[j];
+    b = lower_slot<R>(a, j);
     b.theta_index = a.theta_index;
-    b.sched_op = a.sched_op; b.upd_op = a.upd_op; b.constraint = a.constraint;
-    b.start = a.start; b.end = a.end;
-    b.gated = (a.start > 0 || a.end < (1 << 28)) ? 1 : 0;
-    for (int k = 0; k < 4; ++k) { b.si[k] = a.si[k]; b.ui[k] = a.ui[k]; }
-    b.partner_slot = a.partner_slot; b.partner_index = a.partner_index;
-    b.istate_plane = a.istate_plane; b.istate_init = a.istate_init;
-    if (a.istate_plane >= 0) P.has_istate = 1;
-    b.sf[0] = a.sf[0]; b.sf[1] = a.sf[1];
-    for (int k = 0; k < 6; ++k) b.uf[k] = R(a.uf[k]);
-    b.fast = is_fast_affine(a.upd_op) ? 1 : 0;
-    // ((A y + B) + noise) + C t
-    double A = 1.0, B = 0.0, Ct = 0.0;
-    switch (a.upd_op) {
-      case NSGYM_UPD_ADD: B = a.uf[0]; break;
-      case NSGYM_UPD_ADD_T: Ct = a.uf[0]; break;
-      case NSGYM_UPD_MUL: A = a.uf[0]; break;
-      case NSGYM_UPD_RW: B = a.uf[0]; Ct = a.uf[3]; break;
-      default: break;
-    }
-    b.fa[0] = R(A); b.fa[1] = R(B); b.fa[2] = R(Ct);
-    // `v <= 0` -> v <= 0;  `v < 0` -> v <= -(smallest subnormal);  none -> v <= -inf (never)
-    if (a.constraint == NSGYM_CONS_REJECT_LE0) b.reject_le = R(0);
-    else if (a.constraint == NSGYM_CONS_REJECT_LT0) b.reject_le = -TrueMin<R>::value;
-    else b.reject_le = -std::numeric_limits<R>::infinity();
-    if (j < 2) stochastic01 |= (a.upd_op == NSGYM_UPD_RW || a.upd_op == NSGYM_UPD_OU || a.upd_op == NSGYM_UPD_BRW);
+    b.init = R(spec.theta_init[a.theta_index][0]);
+    b.partner_slot = a.partner_slot;
+    b.partner_default = R(spec.theta_init[a.partner_index >= 0 && a.partner_index < NSGYM_MAX_THETA ? a.partner_index : 0][0]);
+    P.sel[j][a.theta_index] = 0xFFFFFFFFu;
+    P.base[a.theta_index] = R(0);
+    P.bound_mask |= 1 << a.theta_index;
+    if (b.flags & (SF_SLOW_SCHED | SF_SLOW_UPD)) P.slow_j[P.n_slow++] = j;
   }
-  // block 0 of the Philox stream is consumed by next-step autoreset (initial-state draws), by the
-  // normals of slots 0 / 1 and by the gridworld slip draw: compute it once, before any branch
-  P.rng_prefetch = (spec.autoreset == NSGYM_AUTORESET_NEXT_STEP && !is_grid_kind(spec.env_kind)) || stochastic01 ||
-                   is_grid_kind(spec.env_kind);
-  P.pool_f = pools.pool_f; P.pool_i = pools.pool_i; P.bitmap = pools.bitmap;
+  P.n_bound = NP;
   return P;
+}
+
+// gridworlds: slots indexed by theta index (0 = P, 1 = P_left, 2 = P_right), dict position in `lane`
+template <int MAXP>
+static ProgramT<double, MAXP> build_program_by_index(const NsgymSpec& spec, const DevicePools& pools) {
+  ProgramT<double, MAXP> P{};
+  program_common(P, spec, pools);
+  for (int q = 0; q < MAXP; ++q) P.slot[q].istate_plane = -1;
+  for (int j = 0; j < spec.n_slots; ++j) {
+    const int q = spec.slots[j].theta_index;
+    if (q < 0 || q >= MAXP) continue;
+    P.slot[q] = lower_slot<double>(spec.slots[j], j);
+    P.slot[q].theta_index = q;
+    P.bound_mask |= 1 << q;
+    P.n_bound += 1;
+  }
+  return P;
+}
+
+// block 0 of the Philox stream is consumed by next-step autoreset (initial-state draws), by the
+// normals of lanes 0 / 1 and by the gridworld slip draw: compute it once, before any branch
+inline bool wants_prefetch(const NsgymSpec& spec) {
+  if (is_grid_kind(spec.env_kind)) return true;
+  if (spec.autoreset == NSGYM_AUTORESET_NEXT_STEP) return true;
+  for (int j = 0; j < spec.n_slots; ++j)
+    if (slot_draws_block0(spec.slots[j], j)) return true;
+  return false;
 }
 
 template <typename R>
@@ -76,6 +144,7 @@ static StepIO<R> build_io(const LaunchIO& a) {
   io.n = uint32_t(a.n); io.begin = uint32_t(a.begin); io.count = uint32_t(a.count);
   io.gid_offset = a.gid_offset; io.step_index = a.step_index;
   io.skip_updates = a.skip_updates; io.force_init = a.force_init;
+  io.prefetch = (a.prefetch && !a.inj_u && !a.inj_z) ? 1 : 0;
   uint32_t k0 = uint32_t(a.seed), k1 = uint32_t(a.seed >> 32);
   for (int r = 0; r < 10; ++r) {            // Philox4x32 key schedule (Weyl sequence)
     io.rk[r][0] = k0; io.rk[r][1] = k1;
@@ -84,41 +153,48 @@ static StepIO<R> build_io(const LaunchIO& a) {
   return io;
 }
 
-template <typename R, int KIND, int MAXP>
-static cudaError_t launch_classic_kmp(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,
+template <typename R, int KIND, int NP>
+static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,
                                       const LaunchIO& a, cudaStream_t stream) {
-  const ProgramT<R, MAXP> P = build_program<R, MAXP>(spec, pools);
-  const StepIO<R> io = build_io<R>(a);
+  const ProgramT<R, NP> P = build_program<R, NP>(spec, pools);
+  LaunchIO a2 = a;
+  a2.prefetch = wants_prefetch(spec) ? 1 : 0;
+  const StepIO<R> io = build_io<R>(a2);
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
+  // programs without slow-class slots run the lean instantiation (no rule switches compiled in)
+  const bool slow = P.n_slow > 0;
   switch (op) {
-    case OP_STEP: classic_step_kernel<R, KIND, MAXP><<<grid, block, 0, stream>>>(P, io); break;
-    case OP_RESET: classic_reset_kernel<R, KIND, MAXP><<<grid, block, 0, stream>>>(P, io); break;
+    case OP_STEP:
+      if (slow) classic_step_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, io);
+      else classic_step_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, io);
+      break;
+    case OP_RESET: classic_reset_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, io); break;
     case OP_ROLLOUT:
-      classic_rollout_kernel<R, KIND, MAXP><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+      if (slow || NP == 0)
+        classic_rollout_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+      else
+        classic_rollout_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
       break;
   }
   return cudaGetLastError();
 }
 
-// slot-count buckets: registers and unrolled interpreter iterations scale with MAXP
+// one instantiation per exact slot count 0..NTH: the slot loops of the kernels are static
+template <typename R, int KIND, int... NP>
+static cudaError_t launch_classic_np(std::integer_sequence<int, NP...>, LaunchOp op, const NsgymSpec& spec,
+                                     const DevicePools& pools, const LaunchIO& a, cudaStream_t stream) {
+  cudaError_t e = cudaErrorInvalidValue;
+  ((spec.n_slots == NP ? (e = launch_classic_knp<R, KIND, NP>(op, spec, pools, a, stream), 0) : 0), ...);
+  return e;
+}
+
 template <typename R, int KIND>
 static cudaError_t launch_classic_k(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,
                                     const LaunchIO& a, cudaStream_t stream) {
-  constexpr int NTH = KindTraits<KIND>::NTH;
-  const int p = spec.n_slots;
-  if (p > NTH) return cudaErrorInvalidValue;
-  if constexpr (NTH <= 2) {
-    return launch_classic_kmp<R, KIND, 2>(op, spec, pools, a, stream);
-  } else if constexpr (NTH <= 4) {
-    if (p <= 2) return launch_classic_kmp<R, KIND, 2>(op, spec, pools, a, stream);
-    return launch_classic_kmp<R, KIND, 4>(op, spec, pools, a, stream);
-  } else {
-    if (p <= 2) return launch_classic_kmp<R, KIND, 2>(op, spec, pools, a, stream);
-    if (p <= 4) return launch_classic_kmp<R, KIND, 4>(op, spec, pools, a, stream);
-    return launch_classic_kmp<R, KIND, 8>(op, spec, pools, a, stream);
-  }
+  return launch_classic_np<R, KIND>(std::make_integer_sequence<int, KindTraits<KIND>::NTH + 1>{}, op, spec, pools, a,
+                                    stream);
 }
 
 template <typename R>
@@ -140,16 +216,20 @@ static cudaError_t launch_eval_scalar_t(const NsgymSpec& spec, const DevicePools
                                         const int32_t* time, int32_t* istate, uint8_t* flag, void* delta,
                                         const double* inj_u, const double* inj_z, int64_t n, uint64_t seed,
                                         uint64_t step_index, cudaStream_t stream) {
-  const ProgramT<R, 8> P = build_program<R, 8>(spec, pools);
+  ProgramT<R, 1> P{};
+  P.max_steps = spec.max_episode_steps;
+  P.slot[0] = lower_slot<R>(spec.slots[slot], slot);
+  P.slot[0].istate_plane = istate ? 0 : -1;
+  P.n_bound = 1;
+  P.pool_f = pools.pool_f; P.pool_i = pools.pool_i; P.bitmap = pools.bitmap;
   LaunchIO a{};
   a.inj_u = inj_u; a.inj_z = inj_z; a.n = n; a.count = n; a.seed = seed; a.step_index = step_index;
   const StepIO<R> io = build_io<R>(a);
   const int block = 256;
   const unsigned grid = unsigned((n + block - 1) / block);
   if (grid == 0) return cudaSuccess;
-  eval_scalar_update_kernel<R, 8><<<grid, block, 0, stream>>>(P, io, slot,
-                                                              reinterpret_cast<R*>(param), time, istate, flag,
-                                                              reinterpret_cast<R*>(delta));
+  eval_scalar_update_kernel<R><<<grid, block, 0, stream>>>(P, io, reinterpret_cast<R*>(param), time, istate, flag,
+                                                           reinterpret_cast<R*>(delta));
   return cudaGetLastError();
 }
 

@@ -8,20 +8,7 @@ namespace nsg {
 template <int MAXP>
 static GridProgram<MAXP> build_grid_program(const NsgymSpec& spec, const DevicePools& pools) {
   GridProgram<MAXP> G{};
-  // dict-order program first, then permuted so that slot index == theta index
-  const ProgramT<double, 8> dict = build_program<double, 8>(spec, pools);
-  G.base.n_slots = dict.n_slots; G.base.max_steps = dict.max_steps; G.base.autoreset = dict.autoreset;
-  G.base.persistent = dict.persistent; G.base.rng_prefetch = dict.rng_prefetch; G.base.has_istate = dict.has_istate;
-  G.base.pool_f = dict.pool_f; G.base.pool_i = dict.pool_i; G.base.bitmap = dict.bitmap;
-  for (int i = 0; i < 4; ++i) { G.bound[i] = 0; G.plane[i] = 0; }
-  for (int i = 0; i < MAXP; ++i) G.base.slot[i].istate_plane = -1;
-  for (int j = 0; j < dict.n_slots; ++j) {
-    const int idx = dict.slot[j].theta_index;
-    if (idx < 0 || idx >= MAXP) continue;
-    G.base.slot[idx] = dict.slot[j];
-    G.bound[idx] = 1;
-    G.plane[idx] = j;
-  }
+  G.base = build_program_by_index<MAXP>(spec, pools);   // slot index == theta index
   for (int i = 0; i < 3; ++i)
     for (int k = 0; k < NSGYM_MAX_DIST; ++k) G.dist_init[i][k] = spec.theta_init[i][k];
   G.hole_mask = spec.hole_mask; G.goal_mask = spec.goal_mask; G.start_mask = spec.start_mask;
@@ -38,7 +25,9 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
                                  cudaStream_t stream) {
   if (spec.n_slots > MAXP || spec.n_dist != D) return cudaErrorInvalidValue;
   const GridProgram<MAXP> G = build_grid_program<MAXP>(spec, pools);
-  const StepIO<double> io = build_io<double>(a);
+  LaunchIO a2 = a;
+  a2.prefetch = 1;
+  const StepIO<double> io = build_io<double>(a2);
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
@@ -68,18 +57,19 @@ cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, in
                              const int32_t* time, int32_t* istate, uint8_t* flag, double* delta,
                              const double* inj_u, int64_t n, uint64_t seed, uint64_t step_index,
                              cudaStream_t stream) {
-  const GridProgram<3> G = build_grid_program<3>(spec, pools);
+  GridProgram<1> G = build_grid_program<1>(spec, pools);
+  G.base.slot[0] = lower_slot<double>(spec.slots[slot], slot);
+  G.base.bound_mask = 1;
   LaunchIO a{};
   a.inj_u = inj_u; a.n = n; a.count = n; a.seed = seed; a.step_index = step_index;
   const StepIO<double> io = build_io<double>(a);
-  const int index = spec.slots[slot].theta_index;
   const int block = 256;
   const unsigned grid = unsigned((n + block - 1) / block);
   if (grid == 0) return cudaSuccess;
   if (spec.n_dist == 4)
-    eval_dist_update_kernel<4, 3><<<grid, block, 0, stream>>>(G, io, index, param, time, istate, flag, delta);
+    eval_dist_update_kernel<4><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
   else
-    eval_dist_update_kernel<3, 3><<<grid, block, 0, stream>>>(G, io, index, param, time, istate, flag, delta);
+    eval_dist_update_kernel<3><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
   return cudaGetLastError();
 }
 

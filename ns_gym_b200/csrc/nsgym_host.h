@@ -22,7 +22,7 @@ struct LaunchIO {
   const double* inj_u; const double* inj_z; const uint8_t* mask;
   int64_t n, begin, count;
   uint64_t gid_offset, seed, step_index;
-  int32_t skip_updates, force_init;
+  int32_t skip_updates, force_init, prefetch;
   // rollout
   int32_t k_steps; float gamma; float* ret; int32_t* len;
 };
