@@ -48,6 +48,8 @@ WORKLOADS = {
     "c3_mountaincar": dict(case="c3_mountaincar", log2_envs=22, precision="fp32"),
     "c3_pendulum": dict(case="c3_pendulum", log2_envs=22, precision="fp32"),
     "c5_bridge": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64"),
+    # C4: heterogeneous batch, per-env opcode rows, half CartPole (fp32) + half FrozenLake 8x8
+    "c4_hetero": dict(case="c4_cartpole_rows", log2_envs=23, precision="fp32", hetero=True),
     # K-step fused rollouts (state + theta in registers, device-side uniform-random policy)
     "c5_bridge_rollout8": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64", rollout_k=8),
     "c5_bridge_rollout32": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64", rollout_k=32),
@@ -219,6 +221,111 @@ def run_reference(args):
 # ----------------------------------------------------------------------------------------
 # GPU side
 # ----------------------------------------------------------------------------------------
+def synth_rows(kind, template, n, seed):
+    """Per-env rows of the C4 batch, drawn vectorised with numpy (update function from
+    {Increment, Decrement, Trend, Geometric, LinearInterp, RandomWalk} -- gridworld: {Decrement,
+    Increment, UniformDrift, TargetReversion, LinearInterp, StepWise} -- x scheduler from
+    {Continuous, Periodic(2..7), Burst, Window, Discrete}, per-env coefficients).  Returns
+    (rows[n, n_slots], pool_f, pool_i, bitmap): window lists, bitmaps and distribution tables come
+    from shared pools of 1024 entries each."""
+    import numpy as np
+
+    from ns_gym_b200 import native as nv
+    from ns_gym_b200.compile import rows_dtype
+
+    r = np.random.default_rng([4, seed])
+    P = template.spec.n_slots
+    rows = np.zeros((n, P), dtype=rows_dtype())
+    n_pool = 1024
+    # shared pools: windows (4 ints), bitmaps (2 words = 64 event bits), distributions
+    wa = r.integers(0, 10, n_pool); wb = r.integers(12, 40, n_pool)
+    pool_i = np.stack([wa, wa + r.integers(1, 6, n_pool), wb, wb + r.integers(1, 9, n_pool)], 1).astype(np.int32)
+    bitmap = (r.integers(0, 1 << 32, (n_pool, 2), dtype=np.uint64) & r.integers(0, 1 << 32, (n_pool, 2), dtype=np.uint64)
+              & r.integers(0, 1 << 32, (n_pool, 2), dtype=np.uint64)).astype(np.uint32)
+    end_d = r.dirichlet([1.0, 1.0, 1.0], n_pool)
+    start_d = np.tile(np.array([1.0, 0.0, 0.0]), (n_pool, 1))
+    lerp_pool = np.concatenate([start_d, end_d - start_d], 1)                 # 6 doubles per entry
+    step_pool = r.dirichlet([3.0, 1.0, 1.0], (n_pool, 3)).reshape(n_pool, 9)  # up to 3 distributions per entry
+    pool_f = np.concatenate([lerp_pool.reshape(-1), step_pool.reshape(-1)])
+    step_off = lerp_pool.size
+    for j in range(P):
+        key = template.spec.slots[j]
+        col = rows[:, j]
+        col["theta_index"] = key.theta_index
+        col["constraint"] = key.constraint
+        col["partner_slot"] = key.partner_slot
+        col["partner_index"] = key.partner_index
+        col["istate_plane"] = -1
+        col["start"] = 0
+        col["end"] = nv.INT32_MAX
+        sk = r.integers(0, 5, n)
+        si = np.zeros((n, 4), dtype=np.int32)
+        sched = np.zeros(n, dtype=np.int32)
+        m = sk == 1; sched[m] = nv.SCHED_PERIODIC; si[m, 0] = r.integers(2, 8, m.sum())
+        m = sk == 2; sched[m] = nv.SCHED_BURST; cyc = r.integers(2, 7, m.sum()); si[m, 1] = cyc
+        si[m, 0] = 1 + (r.integers(0, 1 << 16, m.sum()) % cyc)
+        m = sk == 3; sched[m] = nv.SCHED_WINDOW; si[m, 0] = 4 * r.integers(0, n_pool, m.sum()); si[m, 1] = 2
+        m = sk == 4; sched[m] = nv.SCHED_BITMAP; si[m, 0] = 2 * r.integers(0, n_pool, m.sum()); si[m, 1] = 64
+        col["sched_op"] = sched
+        col["si"] = si
+        uk = r.integers(0, 6, n)
+        uf = np.zeros((n, 6))
+        ui = np.zeros((n, 4), dtype=np.int32)
+        upd = np.zeros(n, dtype=np.int32)
+        if kind == "grid":
+            m = uk == 0; upd[m] = nv.UPD_D_DEC; uf[m, 0] = r.uniform(0.01, 0.08, m.sum())
+            m = uk == 1; upd[m] = nv.UPD_D_INC; uf[m, 0] = r.uniform(0.0, 0.05, m.sum())
+            m = uk == 2; upd[m] = nv.UPD_D_UNIFORM; rate = r.uniform(0.01, 0.2, m.sum())
+            uf[m, 0] = 1 - rate; uf[m, 1] = rate * (1.0 / 3)
+            m = uk == 3; upd[m] = nv.UPD_D_TARGET; uf[m, 0] = r.uniform(0.05, 0.4, m.sum())
+            uf[m, 1:4] = r.dirichlet([2.0, 1.0, 1.0], m.sum())
+            m = uk == 4; upd[m] = nv.UPD_D_LERP; uf[m, 0] = r.integers(10, 80, m.sum()); ui[m, 0] = 6 * r.integers(0, n_pool, m.sum())
+            m = uk == 5; upd[m] = nv.UPD_D_STEPWISE; ui[m, 0] = step_off + 9 * r.integers(0, n_pool, m.sum())
+            ui[m, 1] = r.integers(1, 4, m.sum())
+            ist = col["istate_plane"]; ist[m] = 0; col["istate_plane"] = ist
+        else:
+            y0 = float(template.spec.theta_init[key.theta_index][0])
+            scale = 0.05 * abs(y0) if y0 else 0.01
+            m = uk == 0; upd[m] = nv.UPD_ADD; uf[m, 0] = r.uniform(0.1, 1.0, m.sum()) * scale
+            m = uk == 1; upd[m] = nv.UPD_ADD; uf[m, 0] = -r.uniform(0.01, 0.2, m.sum()) * scale
+            m = uk == 2; upd[m] = nv.UPD_ADD_T; uf[m, 0] = r.uniform(-0.01, 0.02, m.sum()) * scale
+            m = uk == 3; upd[m] = nv.UPD_MUL; uf[m, 0] = r.uniform(0.98, 1.03, m.sum())
+            m = uk == 4; upd[m] = nv.UPD_LERP; s0 = y0 * r.uniform(0.8, 1.0, m.sum())
+            uf[m, 0] = s0; uf[m, 1] = y0 * r.uniform(1.0, 1.5, m.sum()) - s0; uf[m, 2] = r.integers(20, 200, m.sum())
+            m = uk == 5; upd[m] = nv.UPD_RW; uf[m, 1] = r.uniform(-0.02, 0.02, m.sum()) * scale
+            uf[m, 2] = r.uniform(0.0, 0.3, m.sum()) * scale
+        col["upd_op"] = upd
+        col["uf"] = uf
+        col["ui"] = ui
+        rows[:, j] = col
+    return rows, pool_f, pool_i.reshape(-1), bitmap.reshape(-1)
+
+
+def build_hetero(n_envs, rank, seed=0):
+    """C4: n_envs/2 NS-CartPole (fp32) + n_envs/2 NS-FrozenLake 8x8, every env with its own row."""
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.vector_env import MixedVectorEnv, NSVectorEnv
+    from tests.cases import CASES
+
+    half = n_envs // 2
+    shards = []
+    for k, (name, kind, precision) in enumerate((("c4_cartpole_rows", "classic", "fp32"),
+                                                 ("c4_frozenlake8_rows", "grid", "fp64"))):
+        case = CASES[name]
+        tp = case["params"](PS, PU)
+        from ns_gym_b200.compile import compile_program
+
+        # key-set template: which parameters are bound, their constraints and theta_init
+        tmpl = compile_program(case["env_id"], tp, half, precision=precision, **case["wrapper"], **case["make"])
+        rows, pool_f, pool_i, bitmap = synth_rows(kind, tmpl, half, seed * 1000 + rank * 2 + k)
+        env = NSVectorEnv(case["env_id"], tp, half, precision=precision, autoreset="next_step", seed=seed,
+                          env_id_offset=rank * n_envs + k * half, rows=rows,
+                          pools=(pool_f, pool_i, bitmap), **case["wrapper"], **case["make"])
+        shards.append(env)
+    return MixedVectorEnv(shards), CASES["c4_cartpole_rows"]
+
+
 def build_env(workload, n_envs, rank, seed=0):
     import ns_gym_b200.schedulers as PS
     import ns_gym_b200.update_functions as PU
@@ -226,6 +333,8 @@ def build_env(workload, n_envs, rank, seed=0):
     from tests.cases import CASES
 
     wl = WORKLOADS[workload]
+    if wl.get("hetero"):
+        return build_hetero(n_envs, rank, seed)
     case = CASES[wl["case"]]
     env = NSVectorEnv(case["env_id"], case["params"](PS, PU), n_envs, precision=wl["precision"],
                       autoreset="next_step", seed=seed, env_id_offset=rank * n_envs,
@@ -246,11 +355,13 @@ def random_actions(env, gen_seed):
     return torch.randint(0, N_ACTIONS[kind], (env.num_envs,), generator=g, device=env.device, dtype=torch.int32)
 
 
-def time_steps(env, actions, steps, warmup, dist=None, rollout_k=0):
-    """W untimed + K timed launches, CUDA events on the launching stream; returns seconds."""
+def time_steps(shards, actions, steps, warmup, dist=None, rollout_k=0):
+    """W untimed + K timed steps (one launch per shard per step), CUDA events on the launching
+    stream; returns seconds."""
     import torch
 
     if rollout_k:
+        env = shards[0]
         ret = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
         length = torch.zeros(env.num_envs, dtype=torch.int32, device=env.device)
 
@@ -258,7 +369,8 @@ def time_steps(env, actions, steps, warmup, dist=None, rollout_k=0):
             env.rollout(rollout_k, 1.0, ret, length)
     else:
         def launch():
-            env.step_raw(actions)
+            for s, a in zip(shards, actions):
+                s.step_raw(a)
     return _time_launches(launch, steps, warmup, dist)
 
 
@@ -301,8 +413,10 @@ def run_gpu(args):
     wl = WORKLOADS[args.workload]
     n_envs = 1 << (args.log2_envs or wl["log2_envs"])
     env, case = build_env(args.workload, n_envs, rank, seed=args.seed)
+    shards = list(getattr(env, "shards", [env]))      # C4: one shard (= one kernel launch) per env kind
+    dev = shards[0].device
     env.reset(seed=args.seed)
-    actions = random_actions(env, 1234 + rank)
+    actions = [random_actions(s, 1234 + rank + 17 * k) for k, s in enumerate(shards)]
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
@@ -312,10 +426,10 @@ def run_gpu(args):
     sampler.mark(0)
     rollout_k = int(wl.get("rollout_k", 0))
     per_launch = max(rollout_k, 1)                     # env-steps each env advances per launch
-    secs = time_steps(env, actions, args.steps, max(args.warmup, 3), dist, rollout_k)
+    secs = time_steps(shards, actions, args.steps, max(args.warmup, 3), dist, rollout_k)
     sampler.mark(1)
-    launches = env.launch_count - launches0 - max(args.warmup, 3)
-    t = torch.tensor([secs], dtype=torch.float64, device=env.device)
+    launches = env.launch_count - launches0 - max(args.warmup, 3) * len(shards)
+    t = torch.tensor([secs], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     secs_max = float(t.item())
@@ -328,12 +442,12 @@ def run_gpu(args):
             peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    launch_s = secs / args.steps                       # this rank's average launch duration
+    launch_s = secs / args.steps                       # this rank's average step duration
     bytes_per_launch_env = env.bytes_per_step
     if rollout_k:
         # K fused steps move state / theta / t once per launch and write the return + length
         # accumulators: (2 S w + 2 P w + 8) + 12 per env per launch
-        bytes_per_launch_env = env.bytes_per_step - (env.buffers["action"].element_size() + 4 + 1 + 1) + 12 + 6
+        bytes_per_launch_env = env.bytes_per_step - (shards[0].buffers["action"].element_size() + 4 + 1 + 1) + 12 + 6
     achieved = bytes_per_launch_env * n_envs / launch_s / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -343,33 +457,47 @@ def run_gpu(args):
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": bytes_per_launch_env / per_launch,
-                "kernel_us_per_launch": launch_s * 1e6}
+                "kernel_us_per_launch": launch_s * 1e6 / len(shards)}
+    if len(shards) > 1:
+        roofline["note"] = ("heterogeneous batch: one launch per env kind per step; bytes include the per-env row "
+                            "words read each step: " +
+                            ", ".join(f"{s.program.env_id} {s.bytes_per_step:.0f} B/env-step (rows {s.row_bytes_per_env:.0f} B)"
+                                      for s in shards))
     if rollout_k:
         roofline["note"] = (f"fused {rollout_k}-step rollout: bytes are amortised over K steps, the kernel is "
                             "FP32/FP64-pipe + issue bound, not HBM bound (see profiles/)")
     # ---- end to end through the C-ABI host call ----
-    h_act, h_out = env.make_host_io()
-    h_act.copy_(actions.cpu())
+    host_io = [s.make_host_io() for s in shards]
+    for (h_act, _), a in zip(host_io, actions):
+        h_act.copy_(a.cpu())
+
+    def e2e_step():
+        for s, (h_act, h_out) in zip(shards, host_io):
+            s.step_host(h_act, h_out, n_chunks=args.chunks)
+
     e2e_steps = max(min(args.steps, args.e2e_steps), 1)
     for _ in range(3):
-        env.step_host(h_act, h_out, n_chunks=args.chunks)
+        e2e_step()
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        env.step_host(h_act, h_out, n_chunks=args.chunks)
+        e2e_step()
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
-    t = torch.tensor([e2e_secs], dtype=torch.float64, device=env.device)
+    t = torch.tensor([e2e_secs], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     e2e_value = world * n_envs * e2e_steps / float(t.item())
-    h2d, d2h = env.host_bytes_per_step(h_act, h_out)
+    h2d = d2h = 0
+    for s, (h_act, h_out) in zip(shards, host_io):
+        a_, b_ = s.host_bytes_per_step(h_act, h_out)
+        h2d, d2h = h2d + a_, d2h + b_
     # ---- metric reduction over NCCL (the only collective on this path) ----
-    stats = torch.stack([env.buffers["reward"].double().sum(),
-                         ((env.buffers["flags"] & 3) != 0).double().sum(),
-                         torch.tensor(float(n_envs), dtype=torch.float64, device=env.device)])
+    stats = torch.stack([sum(s.buffers["reward"].double().sum() for s in shards),
+                         sum(((s.buffers["flags"] & 3) != 0).double().sum() for s in shards),
+                         torch.tensor(float(n_envs), dtype=torch.float64, device=dev)])
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     sampler.stop()
@@ -383,12 +511,14 @@ def run_gpu(args):
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32" if wl["precision"] == "fp32" else "f64", "data": "synthetic",
             "config": {
-                "workload": args.workload, "case": wl["case"], "env_id": case["env_id"],
+                "workload": args.workload, "case": wl["case"],
+                "env_id": "+".join(s.program.env_id for s in shards),
                 "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
                 "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k,
                 "parallelism": f"env-shard x{world}, no data-path collective",
                 "l2_policy": f"working set {env.bytes_per_step * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
+                "launches_per_step": len(shards),
             },
             "roofline": roofline,
             "cpu_baseline": cpu,

@@ -175,7 +175,9 @@ typedef struct {
 typedef struct {                 /* bytes the caller must allocate for each bound buffer */
   size_t state, theta, t, istate, action, reward, flags, change, delta, obs;
   int32_t state_words, obs_words, n_istate, theta_planes;
-  double bytes_per_step;         /* algorithmic bytes per env-step, delta & obs as bound */
+  double bytes_per_step;         /* algorithmic bytes per env-step, delta & obs as bound;
+                                    heterogeneous handles include row_bytes_per_env */
+  double row_bytes_per_env;      /* per-env opcode/coefficient row words read each step (0: homogeneous) */
 } NsgymLayout;
 
 typedef struct {
@@ -200,6 +202,16 @@ const char* nsgym_last_error(void);
 
 /* replaces: wrapper construction (base.py:222-294, classic_control.py:27-58, toy_text.py:28-84,282-340,547-603) */
 int nsgym_create(const NsgymSpec* spec, NsgymHandle** out);
+/* Heterogeneous batch (BASELINE config C4: "per-env distinct scheduler/update-function
+ * opcodes"): env e of the handle runs its OWN scheduler / update function for every bound
+ * parameter.  `rows` = NsgymSlot[n_envs][n_slots] in HOST memory, env-major; row (e, j) is what
+ * the wrapper of env e would have been given for its j-th tunable parameter.  The key set is
+ * shared: theta_index, constraint, partner_* and istate_plane of row (e, j) must equal those
+ * of spec->slots[j] (istate_plane >= 0 there if ANY env needs a cursor for slot j); everything
+ * else -- opcodes, range, coefficients, pool offsets, istate_init -- is per env.  The library
+ * lowers the rows, keeps only the words that actually differ between envs as SoA planes in
+ * device memory (owned by the handle) and reports their size in NsgymLayout.row_bytes_per_env. */
+int nsgym_create_rows(const NsgymSpec* spec, const NsgymSlot* rows, NsgymHandle** out);
 void nsgym_destroy(NsgymHandle* h);
 int nsgym_layout(const NsgymHandle* h, int want_delta, int want_obs, NsgymLayout* out);
 int nsgym_bind(NsgymHandle* h, const NsgymBuffers* buffers);

@@ -1,10 +1,11 @@
 """Build ``libnsgym_b200.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-Four translation units, compiled in parallel:
+Five translation units, compiled in parallel:
 
 * ``nsgym_f32.cu``        fp32 fast-mode classic-control kernels (FMA contraction on)
 * ``nsgym_f64.cu``        fp64 parity-mode kernels, ``-fmad=false`` (NumPy rounds every op)
 * ``nsgym_gridworld.cu``  gridworld kernels, ``-fmad=false`` (fp64 cumulative sums / W1)
+* ``nsgym_rows.cu``       lowering of per-env rows (heterogeneous batches, host code)
 * ``nsgym_abi.cu``        the C ABI (host code)
 """
 from __future__ import annotations
@@ -31,6 +32,7 @@ UNITS = {
     "nsgym_f32.cu": [],
     "nsgym_f64.cu": ["-fmad=false"],
     "nsgym_gridworld.cu": ["-fmad=false"],
+    "nsgym_rows.cu": [],
     "nsgym_abi.cu": [],
 }
 
@@ -63,17 +65,22 @@ def is_current() -> bool:
         return f.read().strip() == _source_digest()
 
 
-def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
-    """Compile and link the shared library; returns its path.  No-op when up to date."""
-    if not force and is_current():
+def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool = False,
+                  defines: tuple = (), out: str | None = None) -> str:
+    """Compile and link the shared library; returns its path.  No-op when up to date.
+    ``defines`` / ``out`` build an experimental variant next to the default library."""
+    variant = bool(defines or out)
+    if not force and not variant and is_current():
         return LIB_PATH
     nvcc = _nvcc()
-    os.makedirs(OBJ_DIR, exist_ok=True)
+    lib_path = out or LIB_PATH
+    obj_dir = OBJ_DIR if not variant else os.path.join(LIB_DIR, "obj_" + os.path.basename(lib_path))
+    os.makedirs(obj_dir, exist_ok=True)
 
     def compile_unit(item):
         name, extra = item
-        obj = os.path.join(OBJ_DIR, name.replace(".cu", ".o"))
-        cmd = [nvcc, *ARCH, *COMMON, *extra, "-c", os.path.join(CSRC, name), "-o", obj]
+        obj = os.path.join(obj_dir, name.replace(".cu", ".o"))
+        cmd = [nvcc, *ARCH, *COMMON, *extra, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, name), "-o", obj]
         if ptxas_info:
             cmd[1:1] = ["-Xptxas", "-v"]
         r = subprocess.run(cmd, capture_output=True, text=True)
@@ -85,14 +92,18 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
 
     with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
         objs = list(pool.map(compile_unit, UNITS.items()))
-    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", LIB_PATH, *objs]
+    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", lib_path, *objs]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
-    with open(LIB_PATH + ".sha256", "w") as f:
-        f.write(_source_digest())
-    return LIB_PATH
+    if not variant:
+        with open(LIB_PATH + ".sha256", "w") as f:
+            f.write(_source_digest())
+    return lib_path
 
 
 if __name__ == "__main__":
-    print(build_library(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))
+    _defs = tuple(a[2:] for a in sys.argv if a.startswith("-D"))
+    _out = next((a[6:] for a in sys.argv if a.startswith("--out=")), None)
+    print(build_library(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv,
+                        defines=_defs, out=_out))

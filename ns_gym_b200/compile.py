@@ -149,7 +149,7 @@ class _Pools:
         return off
 
 
-def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, next_plane: list):
+def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, planes: dict, j: int):
     kind = type(sch).__name__
     slot.start, slot.end = _int_bounds(sch.start, sch.end)
     if kind == "ContinuousScheduler":
@@ -189,8 +189,7 @@ def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, next_
     elif kind == "MemorylessScheduler":
         slot.sched_op = nv.SCHED_MEMORYLESS
         slot.sf[0] = float(sch.p)
-        slot.istate_plane = next_plane[0]
-        next_plane[0] += 1
+        slot.istate_plane = planes.setdefault(j, len(planes))
         slot.istate_init = int(np.asarray(sch.transition_time).reshape(-1)[0])
     elif kind == "CustomScheduler":
         # arbitrary Python cannot run on the device: pre-evaluate, in increasing t, only where
@@ -204,16 +203,17 @@ def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, next_
         raise CompileError(f"scheduler {kind} cannot be compiled")
 
 
-def _need_plane(slot, next_plane):
+def _need_plane(slot, planes, j):
+    """One integer state plane per parameter slot (list cursor or Memoryless next-fire time);
+    ``planes`` maps slot position -> plane, allocated on first need."""
     if slot.istate_plane >= 0:
         raise CompileError("a Memoryless scheduler cannot drive a StepWise / Cyclic update "
                            "(one integer state plane per parameter)")
-    slot.istate_plane = next_plane[0]
-    next_plane[0] += 1
+    slot.istate_plane = planes.setdefault(j, len(planes))
     slot.istate_init = 0
 
 
-def _lower_scalar_update(fn, slot, pools, next_plane):
+def _lower_scalar_update(fn, slot, pools, planes, j):
     kind = type(fn).__name__
     uf = slot.uf
     if kind == "IncrementUpdate":
@@ -240,11 +240,11 @@ def _lower_scalar_update(fn, slot, pools, next_plane):
     elif kind == "StepWiseUpdate":
         slot.upd_op = nv.UPD_STEPWISE
         slot.ui[0], slot.ui[1] = pools.add_f(fn.param_list), len(fn.param_list)
-        _need_plane(slot, next_plane)
+        _need_plane(slot, planes, j)
     elif kind == "CyclicUpdate":
         slot.upd_op = nv.UPD_CYCLIC
         slot.ui[0], slot.ui[1] = pools.add_f(fn.value_list), len(fn.value_list)
-        _need_plane(slot, next_plane)
+        _need_plane(slot, planes, j)
     elif kind == "NoUpdate":
         slot.upd_op = nv.UPD_NOP
     elif kind == "RandomWalk":
@@ -266,7 +266,7 @@ def _lower_scalar_update(fn, slot, pools, next_plane):
         raise CompileError(f"update function {kind} cannot drive a scalar parameter")
 
 
-def _lower_dist_update(fn, slot, pools, next_plane, n_dist):
+def _lower_dist_update(fn, slot, pools, planes, j, n_dist):
     kind = type(fn).__name__
     uf = slot.uf
 
@@ -297,12 +297,12 @@ def _lower_dist_update(fn, slot, pools, next_plane, n_dist):
         slot.upd_op = nv.UPD_D_STEPWISE
         flat = [x for d in fn.update_values for x in check(d)]
         slot.ui[0], slot.ui[1] = pools.add_f(flat), len(fn.update_values)
-        _need_plane(slot, next_plane)
+        _need_plane(slot, planes, j)
     elif kind == "DistributionCyclicUpdate":
         slot.upd_op = nv.UPD_D_CYCLIC
         flat = [x for d in fn.dist_list for x in check(d)]
         slot.ui[0], slot.ui[1] = pools.add_f(flat), len(fn.dist_list)
-        _need_plane(slot, next_plane)
+        _need_plane(slot, planes, j)
     elif kind in ("RandomCategorical", "LCBoundedDistrubutionUpdate", "BudgetBoundedIncrement"):
         raise CompileError(f"{kind} is not lowered to the device yet (SURVEY 8(f) rank 4)")
     else:
@@ -345,11 +345,31 @@ def _grid_masks(desc):
     return nrow, ncol, hole, goal, start, starts
 
 
+def _lower_slot(slot, j, key, fn, kind, keys, order, pools, planes, horizon, n_dist):
+    """One (parameter name, update function) pair -> one NsgymSlot."""
+    is_grid = kind in GRID_KINDS
+    slot.theta_index = order.index(key)
+    slot.istate_plane = -1
+    slot.partner_slot = -1
+    slot.partner_index = 0
+    _lower_scheduler(fn.scheduler, slot, pools, horizon, planes, j)
+    if is_grid:
+        _lower_dist_update(fn, slot, pools, planes, j, n_dist)
+    else:
+        _lower_scalar_update(fn, slot, pools, planes, j)
+        slot.constraint = CONSTRAINTS[kind].get(key, nv.CONS_NONE)
+        if slot.constraint in (nv.CONS_ACRO_LENGTH1, nv.CONS_ACRO_COM):
+            partner = ACRO_PARTNER[key]
+            slot.partner_index = order.index(partner)
+            slot.partner_slot = keys.index(partner) if partner in keys else -1
+
+
 def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision: str = "fp32",
                     autoreset: str = "next_step", seed: int = 0, env_id_offset: int = 0,
                     persistent_params: bool = False, max_episode_steps=None, base_params=None,
                     initial_prob_dist=None, modified_rewards=None, terminal_cliff: bool = False,
-                    map_name=None, desc=None, custom_horizon: int = 4096, **_ignored) -> CompiledProgram:
+                    map_name=None, desc=None, custom_horizon: int = 4096, _pools=None, _planes=None,
+                    _finish=True, **_ignored) -> CompiledProgram:
     if env_id not in ENV_TABLE:
         raise CompileError(f"unknown environment id {env_id!r}; supported: {sorted(ENV_TABLE)}")
     kind, env_class, limit = ENV_TABLE[env_id]
@@ -379,25 +399,11 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
     spec.n_dist = n_dist
     horizon = spec.max_episode_steps if spec.max_episode_steps > 0 else int(custom_horizon)
 
-    pools = _Pools()
-    next_plane = [0]
+    pools = _Pools() if _pools is None else _pools
+    planes = {} if _planes is None else _planes
     keys = list(tunable_params.keys())
     for j, (key, fn) in enumerate(tunable_params.items()):
-        slot = spec.slots[j]
-        slot.theta_index = order.index(key)
-        slot.istate_plane = -1
-        slot.partner_slot = -1
-        slot.partner_index = 0
-        _lower_scheduler(fn.scheduler, slot, pools, horizon, next_plane)
-        if is_grid:
-            _lower_dist_update(fn, slot, pools, next_plane, n_dist)
-        else:
-            _lower_scalar_update(fn, slot, pools, next_plane)
-            slot.constraint = CONSTRAINTS[kind].get(key, nv.CONS_NONE)
-            if slot.constraint in (nv.CONS_ACRO_LENGTH1, nv.CONS_ACRO_COM):
-                partner = ACRO_PARTNER[key]
-                slot.partner_index = order.index(partner)
-                slot.partner_slot = keys.index(partner) if partner in keys else -1
+        _lower_slot(spec.slots[j], j, key, fn, kind, keys, order, pools, planes, horizon, n_dist)
 
     # ---- initial values ----
     if not is_grid:
@@ -454,7 +460,17 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
         spec.reward_f, spec.reward_h, spec.reward_g, spec.reward_s = rw["F"], rw["H"], rw["G"], rw["S"]
         spec.terminal_cliff = int(bool(terminal_cliff))
 
-    keep = []
+    prog = CompiledProgram(spec=spec, env_id=env_id, env_kind=kind, env_class=env_class, keys=keys,
+                           precision=int(spec.precision), n_dist=n_dist)
+    prog.horizon = horizon
+    if _finish:
+        _attach_pools(prog, pools)
+    return prog
+
+
+def _attach_pools(prog: CompiledProgram, pools: _Pools):
+    spec = prog.spec
+    keep = prog._keepalive
     if pools.f:
         arr = (C.c_double * len(pools.f))(*pools.f)
         spec.pool_f, spec.n_pool_f = C.cast(arr, C.POINTER(C.c_double)), len(pools.f)
@@ -467,5 +483,44 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
         arr = (C.c_uint32 * len(pools.bits))(*pools.bits)
         spec.bitmap, spec.n_bitmap_words = C.cast(arr, C.POINTER(C.c_uint32)), len(pools.bits)
         keep.append(arr)
-    return CompiledProgram(spec=spec, env_id=env_id, env_kind=kind, env_class=env_class, keys=keys,
-                           precision=int(spec.precision), n_dist=n_dist, _keepalive=keep)
+
+
+def compile_rows(env_id: str, params_per_env, **kwargs):
+    """Heterogeneous batch (BASELINE config C4): ``params_per_env[e]`` is the ``tunable_params``
+    dict env e's wrapper would be given.  Every dict must bind the same parameter names in the
+    same order; schedulers, update functions and their coefficients are free per env.
+
+    Returns ``(CompiledProgram, rows)`` with ``rows`` a C-contiguous numpy structured array
+    ``[n_envs, n_slots]`` of ``NsgymSlot`` records -- the argument of ``nsgym_create_rows``.
+    (Large synthetic batches can fill such an array directly with numpy: ``rows_dtype()``.)"""
+    params_per_env = list(params_per_env)
+    n = len(params_per_env)
+    if n == 0:
+        raise CompileError("empty batch")
+    keys = list(params_per_env[0].keys())
+    if not keys:
+        raise CompileError("a heterogeneous batch needs at least one bound parameter")
+    pools, planes = _Pools(), {}
+    prog = compile_program(env_id, params_per_env[0], n, _pools=pools, _planes=planes, _finish=False, **kwargs)
+    kind, order = prog.env_kind, THETA_ORDER[prog.env_kind]
+    rows = np.zeros((n, len(keys)), dtype=rows_dtype())
+    tmp = nv.NsgymSlot()
+    size = C.sizeof(nv.NsgymSlot)
+    flat = rows.reshape(-1).view(np.uint8).reshape(-1, size)
+    for e, tp in enumerate(params_per_env):
+        if list(tp.keys()) != keys:
+            raise CompileError(f"env {e} binds {list(tp.keys())}, env 0 binds {keys}: the key set is shared")
+        _check_aliasing(tp)
+        for j, (key, fn) in enumerate(tp.items()):
+            C.memset(C.byref(tmp), 0, size)
+            _lower_slot(tmp, j, key, fn, kind, keys, order, pools, planes, prog.horizon, prog.n_dist)
+            flat[e * len(keys) + j] = np.frombuffer(bytes(tmp), dtype=np.uint8)
+    for j in range(len(keys)):                     # a cursor plane exists if ANY env needs one
+        prog.spec.slots[j].istate_plane = planes.get(j, -1)
+    _attach_pools(prog, pools)
+    return prog, rows
+
+
+def rows_dtype():
+    """numpy structured dtype with the memory layout of ``NsgymSlot``."""
+    return np.dtype(nv.NsgymSlot)

@@ -49,6 +49,7 @@ struct NsgymHandle {
   int n_istate = 0;
   cudaStream_t streams[kHostStreams]{};
   bool streams_ready = false;
+  nsg::RowTable rows;              // heterogeneous handles (nsgym_create_rows)
 
   bool grid() const { return nsg::is_grid_kind(spec.env_kind); }
   size_t real_bytes() const { return grid() ? 8 : (spec.precision == NSGYM_F64 ? 8 : 4); }
@@ -70,6 +71,7 @@ nsg::LaunchIO base_io(const NsgymHandle* h) {
   io.n = h->spec.n_envs; io.begin = 0; io.count = h->spec.n_envs;
   io.gid_offset = uint64_t(h->spec.env_id_offset); io.seed = h->spec.seed; io.step_index = h->step_index;
   io.gamma = 1.f;
+  io.rows = h->rows.active ? &h->rows : nullptr;
   return io;
 }
 
@@ -78,6 +80,43 @@ cudaError_t dispatch(NsgymHandle* h, nsg::LaunchOp op, const nsg::LaunchIO& io, 
   if (h->grid()) return nsg::launch_grid(op, h->spec, h->pools, io, s);
   if (h->spec.precision == NSGYM_F64) return nsg::launch_classic_f64(op, h->spec, h->pools, io, s);
   return nsg::launch_classic_f32(op, h->spec, h->pools, io, s);
+}
+
+int validate_slot(const NsgymSpec* s, const NsgymSlot& sl, int j) {
+  const KindInfo& k = kKinds[s->env_kind];
+  const bool grid = nsg::is_grid_kind(s->env_kind);
+  if (sl.theta_index < 0 || sl.theta_index >= k.n_theta) return fail(-1, "slot %d: theta_index out of range", j);
+  if (sl.sched_op < 0 || sl.sched_op >= NSGYM_SCHED_COUNT) return fail(-1, "slot %d: bad sched_op", j);
+  const bool dist_op = sl.upd_op >= NSGYM_UPD_D_NOP;
+  if (dist_op != grid) return fail(-1, "slot %d: update opcode %d does not fit this env kind", j, sl.upd_op);
+  // the Acrobot cross-checks are wired to fixed partners (classic_control.py:241-265, :307-357)
+  if (sl.constraint == NSGYM_CONS_ACRO_LENGTH1 && !(s->env_kind == NSGYM_ENV_ACROBOT && sl.theta_index == 1))
+    return fail(-1, "slot %d: NSGYM_CONS_ACRO_LENGTH1 belongs to Acrobot LINK_LENGTH_1", j);
+  if (sl.constraint == NSGYM_CONS_ACRO_COM &&
+      !(s->env_kind == NSGYM_ENV_ACROBOT && (sl.theta_index == 5 || sl.theta_index == 6)))
+    return fail(-1, "slot %d: NSGYM_CONS_ACRO_COM belongs to Acrobot LINK_COM_POS_1 / LINK_COM_POS_2", j);
+  if (sl.sched_op == NSGYM_SCHED_PERIODIC && sl.si[0] <= 0) return fail(-1, "slot %d: period must be > 0", j);
+  if (sl.sched_op == NSGYM_SCHED_BURST && sl.si[1] <= 0) return fail(-1, "slot %d: burst cycle must be > 0", j);
+  if (sl.sched_op == NSGYM_SCHED_BITMAP &&
+      (sl.si[0] < 0 || (sl.si[0] + (sl.si[1] + 31) / 32) > s->n_bitmap_words))
+    return fail(-1, "slot %d: bitmap range outside the pool", j);
+  if (sl.sched_op == NSGYM_SCHED_WINDOW && (sl.si[0] < 0 || sl.si[0] + 2 * sl.si[1] > s->n_pool_i))
+    return fail(-1, "slot %d: window list outside the pool", j);
+  const int per = dist_op ? s->n_dist : 1;
+  switch (sl.upd_op) {
+    case NSGYM_UPD_POLY: case NSGYM_UPD_STEPWISE: case NSGYM_UPD_CYCLIC:
+    case NSGYM_UPD_D_STEPWISE: case NSGYM_UPD_D_CYCLIC:
+      if (sl.ui[0] < 0 || sl.ui[1] < 0 || sl.ui[0] + sl.ui[1] * per > s->n_pool_f)
+        return fail(-1, "slot %d: value list outside the pool", j);
+      if ((sl.upd_op == NSGYM_UPD_CYCLIC || sl.upd_op == NSGYM_UPD_D_CYCLIC) && sl.ui[1] == 0)
+        return fail(-1, "slot %d: cyclic list is empty", j);
+      break;
+    case NSGYM_UPD_D_LERP:
+      if (sl.ui[0] < 0 || sl.ui[0] + 2 * per > s->n_pool_f) return fail(-1, "slot %d: lerp data outside the pool", j);
+      break;
+    default: break;
+  }
+  return 0;
 }
 
 int validate(const NsgymSpec* s) {
@@ -105,40 +144,9 @@ int validate(const NsgymSpec* s) {
     return fail(-1, "precision must be NSGYM_F32 or NSGYM_F64");
   }
   for (int j = 0; j < s->n_slots; ++j) {
-    const NsgymSlot& sl = s->slots[j];
-    if (sl.theta_index < 0 || sl.theta_index >= k.n_theta) return fail(-1, "slot %d: theta_index out of range", j);
+    if (int rc = validate_slot(s, s->slots[j], j)) return rc;
     for (int q = 0; q < j; ++q)
-      if (s->slots[q].theta_index == sl.theta_index) return fail(-1, "slot %d: parameter bound twice", j);
-    if (sl.sched_op < 0 || sl.sched_op >= NSGYM_SCHED_COUNT) return fail(-1, "slot %d: bad sched_op", j);
-    const bool dist_op = sl.upd_op >= NSGYM_UPD_D_NOP;
-    if (dist_op != grid) return fail(-1, "slot %d: update opcode %d does not fit this env kind", j, sl.upd_op);
-    // the Acrobot cross-checks are wired to fixed partners (classic_control.py:241-265, :307-357)
-    if (sl.constraint == NSGYM_CONS_ACRO_LENGTH1 && !(s->env_kind == NSGYM_ENV_ACROBOT && sl.theta_index == 1))
-      return fail(-1, "slot %d: NSGYM_CONS_ACRO_LENGTH1 belongs to Acrobot LINK_LENGTH_1", j);
-    if (sl.constraint == NSGYM_CONS_ACRO_COM &&
-        !(s->env_kind == NSGYM_ENV_ACROBOT && (sl.theta_index == 5 || sl.theta_index == 6)))
-      return fail(-1, "slot %d: NSGYM_CONS_ACRO_COM belongs to Acrobot LINK_COM_POS_1 / LINK_COM_POS_2", j);
-    if (sl.sched_op == NSGYM_SCHED_PERIODIC && sl.si[0] <= 0) return fail(-1, "slot %d: period must be > 0", j);
-    if (sl.sched_op == NSGYM_SCHED_BURST && sl.si[1] <= 0) return fail(-1, "slot %d: burst cycle must be > 0", j);
-    if (sl.sched_op == NSGYM_SCHED_BITMAP &&
-        (sl.si[0] < 0 || (sl.si[0] + (sl.si[1] + 31) / 32) > s->n_bitmap_words))
-      return fail(-1, "slot %d: bitmap range outside the pool", j);
-    if (sl.sched_op == NSGYM_SCHED_WINDOW && (sl.si[0] < 0 || sl.si[0] + 2 * sl.si[1] > s->n_pool_i))
-      return fail(-1, "slot %d: window list outside the pool", j);
-    const int per = dist_op ? s->n_dist : 1;
-    switch (sl.upd_op) {
-      case NSGYM_UPD_POLY: case NSGYM_UPD_STEPWISE: case NSGYM_UPD_CYCLIC:
-      case NSGYM_UPD_D_STEPWISE: case NSGYM_UPD_D_CYCLIC:
-        if (sl.ui[0] < 0 || sl.ui[1] < 0 || sl.ui[0] + sl.ui[1] * per > s->n_pool_f)
-          return fail(-1, "slot %d: value list outside the pool", j);
-        if ((sl.upd_op == NSGYM_UPD_CYCLIC || sl.upd_op == NSGYM_UPD_D_CYCLIC) && sl.ui[1] == 0)
-          return fail(-1, "slot %d: cyclic list is empty", j);
-        break;
-      case NSGYM_UPD_D_LERP:
-        if (sl.ui[0] < 0 || sl.ui[0] + 2 * per > s->n_pool_f) return fail(-1, "slot %d: lerp data outside the pool", j);
-        break;
-      default: break;
-    }
+      if (s->slots[q].theta_index == s->slots[j].theta_index) return fail(-1, "slot %d: parameter bound twice", j);
   }
   return 0;
 }
@@ -155,6 +163,14 @@ int upload(const T* src, int n, const T** dst) {
 }
 
 }  // namespace
+
+namespace nsg {
+int validate_row_slot(const NsgymSpec* spec, const NsgymSlot* slot, int j, char* err, size_t err_len) {
+  const int rc = validate_slot(spec, *slot, j);
+  if (rc && err && err_len) snprintf(err, err_len, "%s", g_error.c_str());
+  return rc;
+}
+}  // namespace nsg
 
 extern "C" {
 
@@ -183,22 +199,7 @@ int nsgym_create(const NsgymSpec* spec, NsgymHandle** out) {
   NsgymHandle* h = new (std::nothrow) NsgymHandle();
   if (!h) return fail(-3, "out of host memory");
   h->spec = *spec;
-  // fast_mod magic (device: nsgym_device.cuh): exact while t * d < 2^32 over the reachable t
-  {
-    const uint64_t t_max = (spec->autoreset == NSGYM_AUTORESET_NEXT_STEP && spec->max_episode_steps > 0)
-                               ? uint64_t(spec->max_episode_steps) + 1 : (1ull << 28);
-    for (int j = 0; j < spec->n_slots; ++j) {
-      NsgymSlot& sl = h->spec.slots[j];
-      int d = 0;
-      if (sl.sched_op == NSGYM_SCHED_PERIODIC) d = sl.si[0];
-      if (sl.sched_op == NSGYM_SCHED_BURST) d = sl.si[1];
-      if (d >= 2 || sl.sched_op == NSGYM_SCHED_PERIODIC || sl.sched_op == NSGYM_SCHED_BURST) {
-        sl.si[2] = 0;
-        if (d >= 2 && t_max * uint64_t(d) < (1ull << 32))
-          sl.si[2] = int32_t(uint32_t(((1ull << 32) + uint64_t(d) - 1) / uint64_t(d)));
-      }
-    }
-  }
+  for (int j = 0; j < spec->n_slots; ++j) nsg::set_mod_magic(&h->spec.slots[j], *spec);
   int planes = 0;
   for (int j = 0; j < spec->n_slots; ++j)
     if (spec->slots[j].istate_plane >= 0) planes = planes > spec->slots[j].istate_plane + 1 ? planes : spec->slots[j].istate_plane + 1;
@@ -212,8 +213,25 @@ int nsgym_create(const NsgymSpec* spec, NsgymHandle** out) {
   return 0;
 }
 
+int nsgym_create_rows(const NsgymSpec* spec, const NsgymSlot* rows, NsgymHandle** out) {
+  if (!rows) return fail(-1, "rows is NULL");
+  if (spec && spec->n_slots <= 0) return fail(-1, "a heterogeneous batch needs at least one bound parameter");
+  NsgymHandle* h = nullptr;
+  if (int rc = nsgym_create(spec, &h)) return rc;
+  char err[384] = "";
+  const bool dbl = h->grid() || spec->precision == NSGYM_F64;
+  // h->spec keeps the device-side pool pointers out; the rows are lowered against the caller's spec
+  if (int rc = nsg::build_rows(h->spec, rows, dbl, &h->rows, err, sizeof err)) {
+    nsgym_destroy(h);
+    return fail(rc, "%s", err);
+  }
+  *out = h;
+  return 0;
+}
+
 void nsgym_destroy(NsgymHandle* h) {
   if (!h) return;
+  nsg::free_rows(&h->rows);
   cudaFree(const_cast<double*>(h->pools.pool_f));
   cudaFree(const_cast<int32_t*>(h->pools.pool_i));
   cudaFree(const_cast<uint32_t*>(h->pools.bitmap));
@@ -248,6 +266,8 @@ int nsgym_layout(const NsgymHandle* h, int want_delta, int want_obs, NsgymLayout
   if (out->obs) b += 4.0 * k.obs_words;
   if (out->delta) b += double(h->spec.n_slots) * double(w);
   b += 8.0 * h->n_istate;
+  out->row_bytes_per_env = h->rows.active ? h->rows.bytes_per_env : 0.0;
+  b += out->row_bytes_per_env;
   out->bytes_per_step = b;
   return 0;
 }
@@ -350,6 +370,7 @@ int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d
   if (!h || !h->bound) return fail(-1, "handle not bound");
   if (!h->initialised) return fail(-4, "rollout before reset");
   if (policy != 0) return fail(-1, "only policy 0 (uniform random) is implemented");
+  if (h->rows.active) return fail(-5, "fused rollouts of heterogeneous handles are not implemented");
   if (k_steps <= 0) return fail(-1, "k_steps must be positive");
   nsg::LaunchIO io = base_io(h);
   io.k_steps = k_steps;
@@ -368,6 +389,7 @@ int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_
                       int64_t n, void* stream) {
   if (!h) return fail(-1, "NULL handle");
   if (slot < 0 || slot >= h->spec.n_slots) return fail(-1, "slot out of range");
+  if (h->rows.active) return fail(-5, "nsgym_eval_update works on homogeneous handles");
   if (!d_param || !d_time || !d_flag) return fail(-1, "NULL argument");
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   cudaError_t e;

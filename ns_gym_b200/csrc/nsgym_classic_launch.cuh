@@ -123,6 +123,47 @@ static ProgramT<double, MAXP> build_program_by_index(const NsgymSpec& spec, cons
   return P;
 }
 
+// canonical row words of one lowered slot (layout: nsgym_device.cuh, HetT)
+template <typename R>
+static void row_words(const SlotT<R>& b, const NsgymSlot& a, int32_t (&iw)[kRowInt], double (&rw)[kRowReal],
+                      double (&dw)[kRowDbl]) {
+  int flags = b.flags;
+  int mod = 0;
+  if (!(flags & SF_SLOW_SCHED)) {
+    const int on = b.mod_on == INT32_MAX ? 0xFFFF : (b.mod_on < 0 ? 0 : b.mod_on);
+    if (b.mod_d > 0xFFFF || (b.mod_on != INT32_MAX && b.mod_on >= 0xFFFF)) flags |= SF_SLOW_SCHED;   // does not pack
+    else mod = b.mod_d | (on << 16);
+  }
+  iw[RI_OPS] = flags | (a.sched_op << 8) | (a.upd_op << 16);
+  iw[RI_START] = b.start; iw[RI_SPAN] = b.span;
+  iw[RI_MOD] = mod; iw[RI_MAGIC] = (flags & SF_SLOW_SCHED) ? 0 : b.mod_magic;
+  iw[RI_SI0] = a.si[0]; iw[RI_SI1] = a.si[1]; iw[RI_UI0] = a.ui[0]; iw[RI_UI1] = a.ui[1];
+  iw[RI_IINIT] = a.istate_init;
+  if (flags & SF_SLOW_UPD) {
+    for (int k = 0; k < kRowReal; ++k) rw[k] = double(b.uf[k]);
+  } else {
+    rw[0] = double(b.fa[0]); rw[1] = double(b.fa[1]); rw[2] = double(b.fa[2]);
+    rw[3] = double(b.mu); rw[4] = double(b.sigma);
+  }
+  dw[0] = a.sf[0]; dw[1] = a.sf[1];
+}
+
+template <typename R, int NP>
+static HetT<R, NP> build_het(const RowTable& t) {
+  HetT<R, NP> H{};
+  H.ints = t.d_int;
+  H.reals = reinterpret_cast<const R*>(t.d_real);
+  H.dbls = t.d_dbl;
+  for (int j = 0; j < NP; ++j) {
+    H.mask[j] = t.mask[j];
+    for (int w = 0; w < kRowWords; ++w) H.plane[j][w] = t.plane[j][w];
+    for (int w = 0; w < kRowInt; ++w) H.idef[j][w] = t.def_int[j][w];
+    for (int w = 0; w < kRowReal; ++w) H.rdef[j][w] = R(t.def_real[j][w]);
+    for (int w = 0; w < kRowDbl; ++w) H.ddef[j][w] = t.def_dbl[j][w];
+  }
+  return H;
+}
+
 // block 0 of the Philox stream is consumed by next-step autoreset (initial-state draws), by the
 // normals of lanes 0 / 1 and by the gridworld slip draw: compute it once, before any branch
 inline bool wants_prefetch(const NsgymSpec& spec) {
@@ -163,6 +204,18 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
+  if (a.rows && a.rows->active) {       // heterogeneous handle: per-env rows
+    if constexpr (NP == 0) return cudaErrorInvalidValue;
+    else {
+      const HetT<R, NP> H = build_het<R, NP>(*a.rows);
+      switch (op) {
+        case OP_STEP: classic_step_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
+        case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
+        default: return cudaErrorNotSupported;
+      }
+      return cudaGetLastError();
+    }
+  }
   // programs without slow-class slots run the lean instantiation (no rule switches compiled in)
   const bool slow = P.n_slow > 0;
   switch (op) {

@@ -20,6 +20,25 @@ static GridProgram<MAXP> build_grid_program(const NsgymSpec& spec, const DeviceP
   return G;
 }
 
+// the grid program indexes its slots by theta index; the row table by dict position
+template <int MAXP>
+static HetT<double, MAXP> build_het_by_index(const NsgymSpec& spec, const RowTable& t) {
+  HetT<double, MAXP> H{};
+  H.ints = t.d_int;
+  H.reals = reinterpret_cast<const double*>(t.d_real);
+  H.dbls = t.d_dbl;
+  for (int j = 0; j < spec.n_slots; ++j) {
+    const int q = spec.slots[j].theta_index;
+    if (q < 0 || q >= MAXP) continue;
+    H.mask[q] = t.mask[j];
+    for (int w = 0; w < kRowWords; ++w) H.plane[q][w] = t.plane[j][w];
+    for (int w = 0; w < kRowInt; ++w) H.idef[q][w] = t.def_int[j][w];
+    for (int w = 0; w < kRowReal; ++w) H.rdef[q][w] = t.def_real[j][w];
+    for (int w = 0; w < kRowDbl; ++w) H.ddef[q][w] = t.def_dbl[j][w];
+  }
+  return H;
+}
+
 template <int KIND, int D, int MAXP>
 static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& a,
                                  cudaStream_t stream) {
@@ -31,6 +50,15 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
+  if (a.rows && a.rows->active) {
+    const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
+    switch (op) {
+      case OP_STEP: grid_step_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
+      case OP_RESET: grid_reset_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
+      default: return cudaErrorNotSupported;
+    }
+    return cudaGetLastError();
+  }
   switch (op) {
     case OP_STEP: grid_step_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
     case OP_RESET: grid_reset_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;

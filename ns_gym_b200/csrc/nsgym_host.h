@@ -15,6 +15,24 @@ struct DevicePools {
   const uint32_t* bitmap;
 };
 
+// Per-env rows of a heterogeneous handle (nsgym_create_rows): lowered, only the words that vary
+// between envs kept, as SoA planes in device memory owned by the handle.
+constexpr int kRowInt = 10, kRowReal = 5, kRowDbl = 2, kRowWords = kRowInt + kRowReal + kRowDbl;
+struct RowTable {
+  bool active = false;
+  int precision = NSGYM_F32;                // word size of the real planes
+  int32_t* d_int = nullptr;
+  void* d_real = nullptr;
+  double* d_dbl = nullptr;
+  int n_int = 0, n_real = 0, n_dbl = 0;     // plane counts
+  uint32_t mask[NSGYM_MAX_SLOTS] = {};
+  uint8_t plane[NSGYM_MAX_SLOTS][kRowWords] = {};
+  int32_t def_int[NSGYM_MAX_SLOTS][kRowInt] = {};
+  double def_real[NSGYM_MAX_SLOTS][kRowReal] = {};
+  double def_dbl[NSGYM_MAX_SLOTS][kRowDbl] = {};
+  double bytes_per_env = 0.0;
+};
+
 // untyped view of StepIO<R>; the typed launchers reinterpret the real-valued pointers
 struct LaunchIO {
   void* state; void* theta; int32_t* t; int32_t* istate; const void* action;
@@ -25,6 +43,7 @@ struct LaunchIO {
   int32_t skip_updates, force_init, prefetch;
   // rollout
   int32_t k_steps; float gamma; float* ret; int32_t* len;
+  const RowTable* rows;   // heterogeneous handles
 };
 
 // each returns cudaError_t of the launch (cudaGetLastError)
@@ -47,6 +66,30 @@ cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, in
                              const int32_t* time, int32_t* istate, uint8_t* flag, double* delta,
                              const double* inj_u, int64_t n, uint64_t seed, uint64_t step_index,
                              cudaStream_t stream);
+
+// fast_mod magic (device: mod_fire): ceil(2^32 / d), exact while t * d < 2^32 over the reachable t;
+// stored in si[2] of Periodic / Burst slots, 0 = use the real modulo
+inline void set_mod_magic(NsgymSlot* sl, const NsgymSpec& spec) {
+  const uint64_t t_max = (spec.autoreset == NSGYM_AUTORESET_NEXT_STEP && spec.max_episode_steps > 0)
+                             ? uint64_t(spec.max_episode_steps) + 1 : (1ull << 28);
+  int d = 0;
+  if (sl->sched_op == NSGYM_SCHED_PERIODIC) d = sl->si[0];
+  if (sl->sched_op == NSGYM_SCHED_BURST) d = sl->si[1];
+  if (sl->sched_op == NSGYM_SCHED_PERIODIC || sl->sched_op == NSGYM_SCHED_BURST) {
+    sl->si[2] = 0;
+    if (d >= 2 && t_max * uint64_t(d) < (1ull << 32))
+      sl->si[2] = int32_t(uint32_t(((1ull << 32) + uint64_t(d) - 1) / uint64_t(d)));
+  }
+}
+
+// per-slot checks of nsgym_create, reused for every row of nsgym_create_rows (nsgym_abi.cu)
+int validate_row_slot(const NsgymSpec* spec, const NsgymSlot* slot, int j, char* err, size_t err_len);
+
+// lower rows (NsgymSlot[n_envs][n_slots], host) into a RowTable; `real_is_double` selects the
+// word type of the real planes.  Returns 0 or a negative status with `err` filled.
+int build_rows(const NsgymSpec& spec, const NsgymSlot* rows, bool real_is_double, RowTable* out, char* err,
+               size_t err_len);
+void free_rows(RowTable* t);
 
 inline bool is_grid_kind(int k) {
   return k == NSGYM_ENV_FROZENLAKE || k == NSGYM_ENV_CLIFFWALKING || k == NSGYM_ENV_BRIDGE;

@@ -73,7 +73,7 @@ class NsgymLayout(C.Structure):
     _fields_ = [(n, C.c_size_t) for n in
                 ("state", "theta", "t", "istate", "action", "reward", "flags", "change", "delta", "obs")] + [
         ("state_words", C.c_int32), ("obs_words", C.c_int32), ("n_istate", C.c_int32),
-        ("theta_planes", C.c_int32), ("bytes_per_step", C.c_double)]
+        ("theta_planes", C.c_int32), ("bytes_per_step", C.c_double), ("row_bytes_per_env", C.c_double)]
 
 
 class NsgymBuffers(C.Structure):
@@ -88,7 +88,7 @@ class NsgymHostOut(C.Structure):
 
 
 EXPORTS = [
-    "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_destroy",
+    "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
     "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_step_host",
     "nsgym_rollout", "nsgym_eval_update", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
     "nsgym_launch_count",
@@ -102,7 +102,8 @@ class NsgymError(RuntimeError):
 
 
 def lib_path() -> str:
-    return _build.LIB_PATH
+    """In-tree library; ``NSGYM_B200_LIB`` points at an alternative build (kernel experiments)."""
+    return os.environ.get("NSGYM_B200_LIB") or _build.LIB_PATH
 
 
 def load(build_if_missing: bool = False):
@@ -124,6 +125,7 @@ def load(build_if_missing: bool = False):
     lib.nsgym_sizeof.argtypes = [C.c_int]
     lib.nsgym_last_error.restype = C.c_char_p
     lib.nsgym_create.argtypes = [C.POINTER(NsgymSpec), C.POINTER(C.c_void_p)]
+    lib.nsgym_create_rows.argtypes = [C.POINTER(NsgymSpec), C.c_void_p, C.POINTER(C.c_void_p)]
     lib.nsgym_destroy.argtypes = [C.c_void_p]
     lib.nsgym_destroy.restype = None
     lib.nsgym_layout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.POINTER(NsgymLayout)]

@@ -18,7 +18,7 @@ import torch
 
 from . import native as nv
 from .base import Reward
-from .compile import BOX_ACTION, N_ACTIONS, CompiledProgram, compile_program
+from .compile import BOX_ACTION, N_ACTIONS, CompiledProgram, compile_program, compile_rows
 
 
 def _ptr(t: Optional[torch.Tensor]):
@@ -32,7 +32,7 @@ class NSVectorEnv:
                  persistent_params: bool = False, precision: str = "fp32",
                  autoreset: str = "next_step", seed: int = 0, env_id_offset: int = 0,
                  device: Any = None, want_obs: Optional[bool] = None, want_delta: Optional[bool] = None,
-                 **env_kwargs):
+                 rows=None, pools=None, **env_kwargs):
         if delta_change_notification:                         # base.py:252-255
             assert change_notification, (
                 "If change_notification is True, delta_change_notification must be True")
@@ -41,9 +41,37 @@ class NSVectorEnv:
         self.lib = nv.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.num_envs = int(num_envs)
-        self.program: CompiledProgram = compile_program(
-            env_id, tunable_params, num_envs, precision=precision, autoreset=autoreset, seed=seed,
-            env_id_offset=env_id_offset, persistent_params=persistent_params, **env_kwargs)
+        compile_kw = dict(precision=precision, autoreset=autoreset, seed=seed, env_id_offset=env_id_offset,
+                          persistent_params=persistent_params, **env_kwargs)
+        self.rows = None
+        if rows is not None:
+            # heterogeneous batch: `tunable_params` is either one dict per env, or -- with `rows` a
+            # prepared NsgymSlot array [num_envs, n_slots] -- the key-set template of the batch
+            if rows is True:
+                self.program, self.rows = compile_rows(env_id, tunable_params, **compile_kw)
+            else:
+                self.program = compile_program(env_id, tunable_params, num_envs, **compile_kw)
+                self.rows = np.ascontiguousarray(rows)
+                if self.rows.shape != (self.num_envs, len(tunable_params)) or self.rows.dtype.itemsize != C.sizeof(nv.NsgymSlot):
+                    raise ValueError("rows must be an NsgymSlot array of shape [num_envs, n_slots]")
+                for j in range(len(tunable_params)):
+                    if (self.rows["istate_plane"][:, j] >= 0).any() and self.program.spec.slots[j].istate_plane < 0:
+                        planes = 1 + max((self.program.spec.slots[q].istate_plane for q in range(len(tunable_params))),
+                                         default=-1)
+                        self.program.spec.slots[j].istate_plane = planes
+                        sel = self.rows["istate_plane"][:, j] >= 0
+                        self.rows["istate_plane"][sel, j] = planes
+            if len(self.rows) != self.num_envs:
+                raise ValueError(f"{len(self.rows)} rows for {self.num_envs} envs")
+            if pools is not None:
+                # prepared rows index their own pools (pool_f doubles, pool_i int32, bitmap uint32)
+                from .compile import _Pools, _attach_pools
+                pl = _Pools()
+                pl.f, pl.i, pl.bits = list(map(float, pools[0])), list(map(int, pools[1])), list(map(int, pools[2]))
+                self.program._keepalive.clear()
+                _attach_pools(self.program, pl)
+        else:
+            self.program: CompiledProgram = compile_program(env_id, tunable_params, num_envs, **compile_kw)
         self.keys = list(self.program.keys)
         self.change_notification = change_notification
         self.delta_change_notification = delta_change_notification
@@ -58,7 +86,12 @@ class NSVectorEnv:
 
         with torch.cuda.device(self.device):
             h = C.c_void_p()
-            nv.check(self.lib.nsgym_create(C.byref(self.program.spec), C.byref(h)), "nsgym_create")
+            if self.rows is not None:
+                nv.check(self.lib.nsgym_create_rows(C.byref(self.program.spec),
+                                                    C.c_void_p(self.rows.ctypes.data), C.byref(h)),
+                         "nsgym_create_rows")
+            else:
+                nv.check(self.lib.nsgym_create(C.byref(self.program.spec), C.byref(h)), "nsgym_create")
             self._h = h
             kind = self.program.env_kind
             if want_obs is None:
@@ -71,6 +104,7 @@ class NSVectorEnv:
             nv.check(self.lib.nsgym_layout(self._h, int(want_delta), int(want_obs), C.byref(lay)), "nsgym_layout")
             self.layout = lay
             self.bytes_per_step = float(lay.bytes_per_step)
+            self.row_bytes_per_env = float(lay.row_bytes_per_env)
             n, dev = self.num_envs, self.device
             b: dict[str, Optional[torch.Tensor]] = {}
             if self.program.is_grid:
@@ -100,6 +134,13 @@ class NSVectorEnv:
             nv.check(self.lib.nsgym_bind(self._h, C.byref(cb)), "nsgym_bind")
         self._zeros_u8 = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._zeros_real = torch.zeros(n, dtype=self.real, device=self.device)
+
+    @classmethod
+    def heterogeneous(cls, env_id: str, params_per_env, **kwargs):
+        """BASELINE config C4: one ``tunable_params`` dict PER ENV (same parameter names, per-env
+        schedulers / update functions / coefficients)."""
+        params_per_env = list(params_per_env)
+        return cls(env_id, params_per_env, len(params_per_env), rows=True, **kwargs)
 
     # ------------------------------------------------------------------------------------
     def __del__(self):
@@ -297,3 +338,33 @@ class NSVectorEnv:
     def get_default_params(self):
         from .base import TUNABLE_PARAMS
         return TUNABLE_PARAMS[self.program.env_class]
+
+
+class MixedVectorEnv:
+    """Several env kinds in one logical batch (BASELINE config C4: CartPole + FrozenLake with
+    per-env rows).  Envs are bucketed by kind: one ``NSVectorEnv`` shard per kind, each stepped by
+    its own kernel launch on the caller's stream; global env ids (Philox streams) are contiguous
+    per shard.  ``step`` takes / returns one entry per shard, in shard order."""
+
+    def __init__(self, shards):
+        self.shards = list(shards)
+        self.num_envs = sum(s.num_envs for s in self.shards)
+
+    @property
+    def bytes_per_step(self) -> float:
+        """algorithmic bytes per env-step averaged over the batch"""
+        return sum(s.bytes_per_step * s.num_envs for s in self.shards) / self.num_envs
+
+    @property
+    def launch_count(self) -> int:
+        return sum(s.launch_count for s in self.shards)
+
+    def reset(self, *, seed=None, **kw):
+        return [s.reset(seed=seed, **kw) for s in self.shards]
+
+    def step_raw(self, actions=None):
+        for k, s in enumerate(self.shards):
+            s.step_raw(None if actions is None else actions[k])
+
+    def step(self, actions):
+        return [s.step(a) for s, a in zip(self.shards, actions)]

@@ -14,6 +14,11 @@ from . import streams as S_
 from .ns_port import NSEnvPort
 
 
+def params_of(case: dict, S, U, i: int) -> dict:
+    """tunable_params of env ``i``: heterogeneous cases (BASELINE config C4) build one dict per env."""
+    return case["params_of"](S, U, i) if "params_of" in case else case["params"](S, U)
+
+
 def _inject(tunable_params: dict, st: S_.EnvStreams):
     for slot, fn in enumerate(tunable_params.values()):
         if hasattr(fn, "rng"):
@@ -52,7 +57,7 @@ def reference_envs(case: dict, n_envs: int, env_streams=None):
         wrapper_cls = NSClassicControlWrapper
     envs = []
     for i in range(n_envs):
-        tp = case["params"](RS, RU)
+        tp = params_of(case, RS, RU, i)
         if env_streams is not None:
             _inject(tp, env_streams[i])          # before the wrapper clones its template
         env = gym.make(env_id, **make_kw)
@@ -71,7 +76,7 @@ def port_envs(case: dict, n_envs: int, env_streams=None, namespaces=None):
         namespaces = (PS, PU)
     envs = []
     for i in range(n_envs):
-        tp = case["params"](*namespaces)
+        tp = params_of(case, *namespaces, i)
         envs.append(NSEnvPort(case["env_id"], tp, streams=None if env_streams is None else env_streams[i],
                               **case.get("wrapper", {}), **case.get("make", {})))
     return envs

@@ -9,8 +9,133 @@ from __future__ import annotations
 MAP8 = {"map_name": "8x8"}
 
 
+import numpy as np
+
+
 def _c(env_id, params, wrapper=None, make=None, steps=60, fp32_rtol=None):
     return dict(env_id=env_id, params=params, wrapper=wrapper or {}, make=make or {}, steps=steps)
+
+
+def _het(env_id, params_of, wrapper=None, make=None, steps=60):
+    """Heterogeneous case (BASELINE config C4): ``params_of(S, U, e)`` builds the tunable_params
+    of env e; ``params`` (env 0) keeps the homogeneous helpers working."""
+    return dict(env_id=env_id, params=lambda S, U: params_of(S, U, 0), params_of=params_of,
+                wrapper=wrapper or {}, make=make or {}, steps=steps)
+
+
+def params_for(case, S, U, e):
+    """tunable_params of env ``e`` of ``case`` (every env alike unless the case is heterogeneous)."""
+    return case["params_of"](S, U, e) if "params_of" in case else case["params"](S, U)
+
+
+# ---- C4: per-env opcode rows drawn with default_rng(4) (SURVEY 8(d)) --------------------------
+def _c4_scheduler(S, r):
+    k = int(r.integers(0, 5))
+    if k == 0:
+        return S.ContinuousScheduler()
+    if k == 1:
+        return S.PeriodicScheduler(int(r.integers(2, 8)))
+    if k == 2:
+        cycle = int(r.integers(2, 7))
+        return S.BurstScheduler(int(r.integers(1, cycle + 1)), cycle)
+    if k == 3:
+        a, b = int(r.integers(0, 10)), int(r.integers(12, 40))
+        return S.WindowScheduler([(a, a + int(r.integers(1, 6))), (b, b + int(r.integers(1, 9)))])
+    return S.DiscreteScheduler({int(x) for x in r.integers(0, 60, size=int(r.integers(1, 9)))})
+
+
+def _c4_scalar(S, U, r, y0, scale):
+    """one of {Increment, Decrement, Trend, Geometric, LinearInterp, RandomWalk}, coefficients per env"""
+    sch = _c4_scheduler(S, r)
+    k = int(r.integers(0, 6))
+    if k == 0:
+        return U.IncrementUpdate(sch, k=float(r.uniform(0.1, 1.0)) * scale)
+    if k == 1:
+        return U.DecrementUpdate(sch, k=float(r.uniform(0.01, 0.2)) * scale)
+    if k == 2:
+        return U.DeterministicTrend(sch, slope=float(r.uniform(-0.01, 0.02)) * scale)
+    if k == 3:
+        return U.GeometricProgression(sch, r=float(r.uniform(0.98, 1.03)))
+    if k == 4:
+        return U.LinearInterpolation(sch, y0 * float(r.uniform(0.8, 1.0)), y0 * float(r.uniform(1.0, 1.5)),
+                                     T=int(r.integers(20, 200)))
+    return U.RandomWalk(sch, mu=float(r.uniform(-0.02, 0.02)) * scale, sigma=float(r.uniform(0.0, 0.3)) * scale)
+
+
+def _c4_cartpole(S, U, e):
+    r = np.random.default_rng([4, e])
+    return {"masspole": _c4_scalar(S, U, r, 0.1, 0.01), "gravity": _c4_scalar(S, U, r, 9.8, 0.5)}
+
+
+def _c4_frozenlake(S, U, e):
+    r = np.random.default_rng([4, 1 << 20, e])
+    sch = _c4_scheduler(S, r)
+    k = int(r.integers(0, 6))
+    if k == 0:
+        fn = U.DistributionDecrementUpdate(sch, k=float(r.uniform(0.01, 0.08)))
+    elif k == 1:
+        fn = U.DistributionIncrementUpdate(sch, k=float(r.uniform(0.0, 0.05)))
+    elif k == 2:
+        fn = U.UniformDrift(sch, rate=float(r.uniform(0.01, 0.2)))
+    elif k == 3:
+        tgt = r.dirichlet([2.0, 1.0, 1.0])
+        fn = U.TargetReversion(sch, target=[float(x) for x in tgt], theta=float(r.uniform(0.05, 0.4)))
+    elif k == 4:
+        end = r.dirichlet([1.0, 1.0, 1.0])
+        fn = U.DistributionLinearInterpolation(sch, [1.0, 0.0, 0.0], [float(x) for x in end],
+                                               T=int(r.integers(10, 80)))
+    else:
+        vals = [[float(x) for x in r.dirichlet([3.0, 1.0, 1.0])] for _ in range(int(r.integers(1, 4)))]
+        fn = U.DistributionStepWiseUpdate(sch, vals)
+    return {"P": fn}
+
+
+def _het_cartpole_wide(S, U, e):
+    """every scalar opcode and every scheduler, mixed per env (cursors, stochastic schedulers, slow rules)"""
+    r = np.random.default_rng([5, e])
+    scheds = [
+        lambda: S.ContinuousScheduler(start=int(r.integers(0, 4)), end=int(r.integers(20, 70))),
+        lambda: S.PeriodicScheduler(int(r.integers(1, 5))),
+        lambda: S.RandomScheduler(probability=float(r.uniform(0.2, 0.9)), seed=e),
+        lambda: S.DecayingProbabilityScheduler(float(r.uniform(0.5, 1.0)), float(r.uniform(0.01, 0.1)), seed=e),
+        lambda: S.MemorylessScheduler(p=float(r.uniform(0.2, 0.6)), seed=e),
+        lambda: S.BurstScheduler(2, 5),
+    ]
+
+    def sch():
+        return scheds[int(r.integers(0, len(scheds)))]()
+
+    def upd(y0, scale, allow_cursor):
+        k = int(r.integers(0, 9 if allow_cursor else 7))
+        if k == 0:
+            return U.OrnsteinUhlenbeck(sch(), theta=float(r.uniform(0.05, 0.3)), mu=y0, sigma=float(r.uniform(0, 0.05)) * scale)
+        if k == 1:
+            return U.BoundedRandomWalk(sch(), mu=0.0, sigma=0.2 * scale, lo=0.8 * y0, hi=1.2 * y0)
+        if k == 2:
+            return U.SigmoidTransition(sch(), a=y0, b=y0 * 1.3, k=float(r.uniform(0.1, 1.0)), t0=int(r.integers(5, 30)))
+        if k == 3:
+            return U.PolynomialTrend(sch(), coeffs=[1e-3 * scale, float(r.uniform(-1, 1)) * 1e-5 * scale])
+        if k == 4:
+            return U.OscillatingUpdate(sch(), delta=float(r.uniform(0.01, 0.1)) * scale)
+        if k == 5:
+            return U.ExponentialDecay(sch(), decay_rate=float(r.uniform(1e-4, 1e-3)))
+        if k == 6:
+            return U.RandomWalkWithDriftAndTrend(sch(), alpha=0.001 * scale, mu=0.0, sigma=0.05 * scale, slope=1e-4 * scale)
+        s2 = S.PeriodicScheduler(int(r.integers(1, 4)))       # cursor updates: deterministic scheduler
+        vals = [y0 * float(r.uniform(0.7, 1.4)) for _ in range(int(r.integers(1, 5)))]
+        return U.StepWiseUpdate(s2, vals) if k == 7 else U.CyclicUpdate(s2, vals)
+
+    return {"length": upd(0.5, 0.5, True), "force_mag": upd(10.0, 1.0, False), "masscart": upd(1.0, 1.0, True)}
+
+
+def _het_bridge(S, U, e):
+    r = np.random.default_rng([6, e])
+    left = U.UniformDrift(S.PeriodicScheduler(int(r.integers(1, 4))), rate=float(r.uniform(0.01, 0.1)))
+    if int(r.integers(0, 2)):
+        right = U.DistributionDecrementUpdate(S.ContinuousScheduler(), k=float(r.uniform(0.005, 0.03)))
+    else:
+        right = U.DistributionCyclicUpdate(S.BurstScheduler(1, 3), [[0.8, 0.1, 0.1], [0.5, 0.25, 0.25]])
+    return {"P_left": left, "P_right": right}
 
 
 CASES = {
@@ -215,4 +340,19 @@ CASES = {
         lambda S, U: {"P": U.UniformDrift(S.PeriodicScheduler(3), rate=0.1)},
         wrapper=dict(initial_prob_dist=[0.7, 0.1, 0.1, 0.1], change_notification=True,
                      delta_change_notification=True, terminal_cliff=True), steps=120),
+    # ---- C4: heterogeneous batches (per-env rows) ---------------------------------------------------
+    "c4_cartpole_rows": _het(
+        "CartPole-v1", _c4_cartpole,
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=90),
+    "c4_frozenlake8_rows": _het(
+        "FrozenLake-v1", _c4_frozenlake,
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True, delta_change_notification=True),
+        make=dict(MAP8, max_episode_steps=200), steps=150),
+    "het_cartpole_wide": _het(
+        "CartPole-v1", _het_cartpole_wide,
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),
+    "het_bridge_split": _het(
+        "ns_gym/Bridge-v0", _het_bridge,
+        wrapper=dict(initial_prob_dist=([0.9, 0.05, 0.05], [1.0, 0.0, 0.0]),
+                     change_notification=True, delta_change_notification=True), steps=100),
 }

@@ -1,6 +1,6 @@
 """Generate golden vectors from the REAL reference (run in the build container only).
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py [case ...]      # no names: every case
 
 For every case of tests/cases.py this imports /root/reference/ns_gym verbatim on top of the
 restated gymnasium shim (oracle/ref_loader.py), injects pre-drawn uniform / normal tables
@@ -28,7 +28,10 @@ SEED = 101
 def main():
     assert ref_loader.available(), "the reference tree is needed to (re)generate golden vectors"
     out_dir = os.path.dirname(os.path.abspath(__file__))
+    only = set(sys.argv[1:])
     for name, case in sorted(CASES.items()):
+        if only and name not in only:
+            continue
         K = case["steps"]
         actions = harness.draw_actions(case, SEED + 1, K, N_ENVS)
         clock, per_env, u, z = harness.make_streams(SEED, N_ENVS, K + 1, n_slots_of(case))

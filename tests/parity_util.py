@@ -36,9 +36,12 @@ def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_ste
     from ns_gym_b200.vector_env import NSVectorEnv
     from ns_gym_b200 import native as nv
 
-    tp = case["params"](PS, PU)
-    env = NSVectorEnv(case["env_id"], tp, n_envs, precision=precision, autoreset=autoreset,
-                      want_delta=True, want_obs=True, **case.get("wrapper", {}), **case.get("make", {}))
+    kw = dict(precision=precision, autoreset=autoreset, want_delta=True, want_obs=True,
+              **case.get("wrapper", {}), **case.get("make", {}))
+    if "params_of" in case:       # heterogeneous batch: one tunable_params dict per env (nsgym_create_rows)
+        env = NSVectorEnv.heterogeneous(case["env_id"], [case["params_of"](PS, PU, e) for e in range(n_envs)], **kw)
+    else:
+        env = NSVectorEnv(case["env_id"], case["params"](PS, PU), n_envs, **kw)
     dev = env.device
     U = torch.as_tensor(u, dtype=torch.float64, device=dev).contiguous()
     Z = torch.as_tensor(z, dtype=torch.float64, device=dev).contiguous()
