@@ -236,9 +236,32 @@ int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* ou
  * (MCTS-style random rollouts, benchmark_algorithms/MCTS.py:162-181).  policy 0 = uniform
  * random action.  d_return float[N] += sum of rewards (discounted by gamma^k);
  * d_length int32[N] += steps taken before the first episode end.  With
- * NSGYM_AUTORESET_NEXT_STEP envs keep cycling through episodes inside the K steps. */
+ * NSGYM_AUTORESET_NEXT_STEP envs keep cycling through episodes inside the K steps; with
+ * NSGYM_AUTORESET_NONE a lane stops at its first episode end (MCTS default policy,
+ * MCTS.py:162-181) and a lane that had already ended contributes nothing. */
 int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d_return,
                   int32_t* d_length, int skip_updates, void* stream);
+
+/* Planning envs.
+ * replaces: get_planning_env + __deepcopy__ (classic_control.py:120-186, toy_text.py:471-511,
+ * 669-711) for a batch, with the fan-out MCTS-style consumers need (benchmark_algorithms/MCTS.py:
+ * 130-131 makes one deepcopy per simulation): lane r * fanout + k of `dst` becomes a copy of env r
+ * of `src` -- state, episode time, parameters / sampling table, list cursors.  `dst` must be a
+ * bound handle of the same env kind, precision and slot list with src.n_envs * fanout envs.
+ * theta_from_init != 0: the planner is not told the current parameters
+ * (delta_change_notification False): theta <- initial values, cursors still carried.
+ * The copy starts a fresh TimeLimit count (the reference builds a new gym.make chain), while
+ * the NS time t carries on; dst is left "reset" and steps / rolls out like any handle (use
+ * skip_updates for in_sim_change False).  Philox streams of dst are keyed by dst's own seed. */
+int nsgym_fanout(const NsgymHandle* src, NsgymHandle* dst, int fanout, int theta_from_init, void* stream);
+
+/* Device-side snapshot / restore of everything a step mutates (state, theta, t, cursors), packed
+ * in that order into a caller buffer of nsgym_snapshot_bytes(); the Philox step counter travels
+ * through *step_index.  restore(snapshot(x)) followed by the same calls reproduces the same
+ * results bit for bit. */
+size_t nsgym_snapshot_bytes(const NsgymHandle* h);
+int nsgym_snapshot(NsgymHandle* h, void* d_dst, uint64_t* step_index, void* stream);
+int nsgym_restore(NsgymHandle* h, const void* d_src, uint64_t step_index, void* stream);
 
 /* Fire-test + advance stages only (a1 + a2/a3), for known-answer checks of the update
  * functions: applies slot `slot` to d_param (real[N] scalars, or double[D][N]) at times

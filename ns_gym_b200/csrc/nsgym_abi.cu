@@ -50,6 +50,7 @@ struct NsgymHandle {
   cudaStream_t streams[kHostStreams]{};
   bool streams_ready = false;
   nsg::RowTable rows;              // heterogeneous handles (nsgym_create_rows)
+  int32_t plan_elapsed = -1;       // planning copy (nsgym_fanout): TimeLimit steps since the copy
 
   bool grid() const { return nsg::is_grid_kind(spec.env_kind); }
   size_t real_bytes() const { return grid() ? 8 : (spec.precision == NSGYM_F64 ? 8 : 4); }
@@ -72,6 +73,7 @@ nsg::LaunchIO base_io(const NsgymHandle* h) {
   io.gid_offset = uint64_t(h->spec.env_id_offset); io.seed = h->spec.seed; io.step_index = h->step_index;
   io.gamma = 1.f;
   io.rows = h->rows.active ? &h->rows : nullptr;
+  io.plan_elapsed = h->plan_elapsed;
   return io;
 }
 
@@ -161,6 +163,42 @@ int upload(const T* src, int n, const T** dst) {
   *dst = d;
   return 0;
 }
+
+}  // namespace
+
+namespace {
+
+// lane i of dst <- env i / fanout of src, `words` 32-bit words per env record (packed records)
+__global__ void fanout_records_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint64_t total,
+                                      uint32_t words, uint32_t fanout) {
+  const uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const uint64_t env = idx / words;
+  const uint32_t w = uint32_t(idx - env * words);
+  dst[idx] = src[(env / fanout) * words + w];
+}
+// plane layout [planes][n]: dst[p][i] <- src[p][i / fanout] (or a constant per plane)
+__global__ void fanout_planes_kernel(const uint32_t* __restrict__ src, uint32_t* __restrict__ dst, uint32_t n_dst,
+                                     uint32_t n_src, uint32_t planes, uint32_t words, uint32_t fanout,
+                                     uint32_t and_mask) {
+  const uint64_t idx = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;     // over n_dst * words
+  if (idx >= uint64_t(n_dst) * words) return;
+  const uint32_t i = uint32_t(idx / words), w = uint32_t(idx % words);
+  for (uint32_t p = 0; p < planes; ++p)
+    dst[(uint64_t(p) * n_dst + i) * words + w] = src[(uint64_t(p) * n_src + i / fanout) * words + w] & and_mask;
+}
+struct PlaneConsts { uint32_t lo[NSGYM_MAX_SLOTS * NSGYM_MAX_DIST], hi[NSGYM_MAX_SLOTS * NSGYM_MAX_DIST]; };
+__global__ void fill_planes_kernel(uint32_t* __restrict__ dst, uint32_t n_dst, uint32_t planes, uint32_t words,
+                                   const __grid_constant__ PlaneConsts c) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_dst) return;
+  for (uint32_t p = 0; p < planes; ++p) {
+    dst[(uint64_t(p) * n_dst + i) * words] = c.lo[p];
+    if (words == 2) dst[(uint64_t(p) * n_dst + i) * words + 1] = c.hi[p];
+  }
+}
+
+inline unsigned blocks_for(uint64_t n) { return unsigned((n + 255) / 256); }
 
 }  // namespace
 
@@ -296,6 +334,7 @@ int nsgym_reset(NsgymHandle* h, const uint8_t* d_mask, const double* d_inj_unifo
   if (e != cudaSuccess) return fail(-10, "reset launch: %s", cudaGetErrorString(e));
   h->initialised = true;
   h->step_index += 1;
+  if (!d_mask) h->plan_elapsed = -1;   // a full reset restarts TimeLimit and t together
   return 0;
 }
 
@@ -311,6 +350,7 @@ int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform
   cudaError_t e = dispatch(h, nsg::OP_STEP, io, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(-10, "step launch: %s", cudaGetErrorString(e));
   h->step_index += 1;
+  if (h->plan_elapsed >= 0) h->plan_elapsed += 1;
   return 0;
 }
 
@@ -362,6 +402,7 @@ int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* ou
   }
   for (auto& s : h->streams) NSG_CUDA(cudaStreamSynchronize(s));
   h->step_index += 1;
+  if (h->plan_elapsed >= 0) h->plan_elapsed += 1;
   return 0;
 }
 
@@ -381,6 +422,112 @@ int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d
   cudaError_t e = dispatch(h, nsg::OP_ROLLOUT, io, static_cast<cudaStream_t>(stream));
   if (e != cudaSuccess) return fail(-10, "rollout launch: %s", cudaGetErrorString(e));
   h->step_index += uint64_t(k_steps);
+  if (h->plan_elapsed >= 0) h->plan_elapsed += k_steps;
+  return 0;
+}
+
+int nsgym_fanout(const NsgymHandle* src, NsgymHandle* dst, int fanout, int theta_from_init, void* stream) {
+  if (!src || !dst || !src->bound || !dst->bound) return fail(-1, "both handles must be bound");
+  if (!src->initialised) return fail(-4, "the source must be reset before a planning copy is taken");
+  if (fanout < 1) return fail(-1, "fanout must be >= 1");
+  const NsgymSpec &a = src->spec, &b = dst->spec;
+  if (a.env_kind != b.env_kind || a.precision != b.precision || a.n_slots != b.n_slots || a.n_dist != b.n_dist ||
+      src->n_istate != dst->n_istate)
+    return fail(-1, "planning copy: source and destination differ in env kind / precision / slot list");
+  for (int j = 0; j < a.n_slots; ++j)
+    if (a.slots[j].theta_index != b.slots[j].theta_index || a.slots[j].istate_plane != b.slots[j].istate_plane)
+      return fail(-1, "planning copy: slot %d differs between source and destination", j);
+  if (b.n_envs != a.n_envs * int64_t(fanout))
+    return fail(-1, "planning copy: destination has %lld envs, expected %lld x %d", (long long)b.n_envs,
+                (long long)a.n_envs, fanout);
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const uint32_t n_src = uint32_t(a.n_envs), n_dst = uint32_t(b.n_envs), m = uint32_t(fanout);
+  // state: one packed record per env
+  {
+    const uint32_t words = uint32_t(src->state_bytes_per_env() / 4);
+    const uint64_t total = uint64_t(n_dst) * words;
+    fanout_records_kernel<<<blocks_for(total), 256, 0, s>>>(static_cast<const uint32_t*>(src->buf.d_state),
+                                                           static_cast<uint32_t*>(dst->buf.d_state), total, words, m);
+  }
+  // episode time word: time, "ended" and "table fresh" bits carry over; CartPole's "terminated
+  // once" does not (the copy is a freshly reset env whose state is overwritten)
+  fanout_planes_kernel<<<blocks_for(n_dst), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(src->buf.d_t),
+                                                        reinterpret_cast<uint32_t*>(dst->buf.d_t), n_dst, n_src, 1, 1, m,
+                                                        ~0x40000000u);
+  if (src->n_istate > 0)
+    fanout_planes_kernel<<<blocks_for(n_dst), 256, 0, s>>>(reinterpret_cast<const uint32_t*>(src->buf.d_istate),
+                                                          reinterpret_cast<uint32_t*>(dst->buf.d_istate), n_dst, n_src,
+                                                          uint32_t(src->n_istate), 1, m, ~0u);
+  const int planes = src->theta_planes();
+  if (planes > 0) {
+    const uint32_t words = uint32_t(src->real_bytes() / 4);
+    if (!theta_from_init) {
+      fanout_planes_kernel<<<blocks_for(uint64_t(n_dst) * words), 256, 0, s>>>(
+          static_cast<const uint32_t*>(src->buf.d_theta), static_cast<uint32_t*>(dst->buf.d_theta), n_dst, n_src,
+          uint32_t(planes), words, m, ~0u);
+    } else {
+      // classic_control.py:131-135 / toy_text.py:477-481, 675-682: parameters back to their initial values
+      PlaneConsts c{};
+      const int per = src->grid() ? a.n_dist : 1;
+      for (int j = 0; j < a.n_slots; ++j)
+        for (int k = 0; k < per; ++k) {
+          const double v = a.theta_init[a.slots[j].theta_index][k];
+          uint32_t lo, hi = 0;
+          if (words == 2) { uint64_t u; std::memcpy(&u, &v, 8); lo = uint32_t(u); hi = uint32_t(u >> 32); }
+          else { const float f = float(v); std::memcpy(&lo, &f, 4); }
+          c.lo[j * per + k] = lo; c.hi[j * per + k] = hi;
+        }
+      fill_planes_kernel<<<blocks_for(n_dst), 256, 0, s>>>(static_cast<uint32_t*>(dst->buf.d_theta), n_dst,
+                                                          uint32_t(planes), words, c);
+    }
+  }
+  NSG_CUDA(cudaGetLastError());
+  dst->initialised = true;
+  dst->plan_elapsed = 0;
+  dst->launches += 3;
+  return 0;
+}
+
+size_t nsgym_snapshot_bytes(const NsgymHandle* h) {
+  if (!h) return 0;
+  const size_t n = size_t(h->spec.n_envs);
+  return n * h->state_bytes_per_env() + n * size_t(h->theta_planes()) * h->real_bytes() + n * 4 +
+         n * size_t(h->n_istate) * 4;
+}
+
+namespace {
+int snapshot_copy(NsgymHandle* h, char* packed, bool to_packed, cudaStream_t s) {
+  const size_t n = size_t(h->spec.n_envs);
+  struct Part { void* dev; size_t bytes; } parts[4] = {
+      {h->buf.d_state, n * h->state_bytes_per_env()},
+      {h->buf.d_theta, n * size_t(h->theta_planes()) * h->real_bytes()},
+      {h->buf.d_t, n * 4},
+      {h->buf.d_istate, n * size_t(h->n_istate) * 4}};
+  size_t off = 0;
+  for (const Part& p : parts) {
+    if (p.bytes && p.dev) {
+      if (to_packed) NSG_CUDA(cudaMemcpyAsync(packed + off, p.dev, p.bytes, cudaMemcpyDeviceToDevice, s));
+      else NSG_CUDA(cudaMemcpyAsync(p.dev, packed + off, p.bytes, cudaMemcpyDeviceToDevice, s));
+    }
+    off += p.bytes;
+  }
+  return 0;
+}
+}  // namespace
+
+int nsgym_snapshot(NsgymHandle* h, void* d_dst, uint64_t* step_index, void* stream) {
+  if (!h || !h->bound || !d_dst) return fail(-1, "NULL argument / handle not bound");
+  if (step_index) *step_index = h->step_index;
+  return snapshot_copy(h, static_cast<char*>(d_dst), true, static_cast<cudaStream_t>(stream));
+}
+
+int nsgym_restore(NsgymHandle* h, const void* d_src, uint64_t step_index, void* stream) {
+  if (!h || !h->bound || !d_src) return fail(-1, "NULL argument / handle not bound");
+  if (int rc = snapshot_copy(h, const_cast<char*>(static_cast<const char*>(d_src)), false,
+                             static_cast<cudaStream_t>(stream)))
+    return rc;
+  h->step_index = step_index;
+  h->initialised = true;
   return 0;
 }
 

@@ -186,6 +186,7 @@ static StepIO<R> build_io(const LaunchIO& a) {
   io.gid_offset = a.gid_offset; io.step_index = a.step_index;
   io.skip_updates = a.skip_updates; io.force_init = a.force_init;
   io.prefetch = (a.prefetch && !a.inj_u && !a.inj_z) ? 1 : 0;
+  io.plan_elapsed = a.plan_elapsed;
   uint32_t k0 = uint32_t(a.seed), k1 = uint32_t(a.seed >> 32);
   for (int r = 0; r < 10; ++r) {            // Philox4x32 key schedule (Weyl sequence)
     io.rk[r][0] = k0; io.rk[r][1] = k1;

@@ -40,7 +40,7 @@ struct LaunchIO {
   const double* inj_u; const double* inj_z; const uint8_t* mask;
   int64_t n, begin, count;
   uint64_t gid_offset, seed, step_index;
-  int32_t skip_updates, force_init, prefetch;
+  int32_t skip_updates, force_init, prefetch, plan_elapsed;
   // rollout
   int32_t k_steps; float gamma; float* ret; int32_t* len;
   const RowTable* rows;   // heterogeneous handles

@@ -90,7 +90,7 @@ class NsgymHostOut(C.Structure):
 EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
     "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_step_host",
-    "nsgym_rollout", "nsgym_eval_update", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
+    "nsgym_rollout", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_eval_update", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
     "nsgym_launch_count",
 ]
 
@@ -119,6 +119,9 @@ def load(build_if_missing: bool = False):
             raise NsgymError(
                 f"{path} not found: build the CUDA library first (python -m ns_gym_b200.build or "
                 "__graft_entry__.build()); ns_gym_b200 has no CPU fallback")
+    if path == _build.LIB_PATH and not _build.is_current():
+        raise NsgymError(f"{path} is older than the sources under ns_gym_b200/csrc: rebuild it "
+                         "(python -m ns_gym_b200.build or __graft_entry__.build())")
     lib = C.CDLL(path)
     lib.nsgym_abi_version.restype = C.c_int
     lib.nsgym_sizeof.restype = C.c_size_t
@@ -135,6 +138,11 @@ def load(build_if_missing: bool = False):
     lib.nsgym_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymHostOut), C.c_int]
     lib.nsgym_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p]
+    lib.nsgym_fanout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
+    lib.nsgym_snapshot_bytes.restype = C.c_size_t
+    lib.nsgym_snapshot_bytes.argtypes = [C.c_void_p]
+    lib.nsgym_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
+    lib.nsgym_restore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.nsgym_eval_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]

@@ -38,6 +38,13 @@ class NSVectorEnv:
                 "If change_notification is True, delta_change_notification must be True")
         if not torch.cuda.is_available():
             raise nv.NsgymError("ns_gym_b200 needs a CUDA device: there is no CPU execution path")
+        # what a planning copy is rebuilt from (get_planning_env)
+        self._ctor = dict(env_id=env_id, tunable_params=tunable_params, num_envs=int(num_envs),
+                          change_notification=change_notification,
+                          delta_change_notification=delta_change_notification, in_sim_change=in_sim_change,
+                          scalar_reward=scalar_reward, persistent_params=persistent_params, precision=precision,
+                          seed=seed, device=device, want_obs=want_obs, want_delta=want_delta, rows=rows,
+                          pools=pools, env_kwargs=dict(env_kwargs))
         self.lib = nv.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.num_envs = int(num_envs)
@@ -324,6 +331,67 @@ class NSVectorEnv:
         h2d = h_actions.numel() * h_actions.element_size()
         d2h = sum(t.numel() * t.element_size() for t in h_out.values())
         return h2d, d2h
+
+    # ---- planning copies (classic_control.py:120-186, toy_text.py:471-511, 669-711) ----
+    # TimeLimit of the gym.make chain the reference's __deepcopy__ builds
+    _PLANNING_LIMIT = {nv.ENV_FROZENLAKE: 100, nv.ENV_CLIFFWALKING: 1000, nv.ENV_BRIDGE: 1000}
+
+    def get_planning_env(self, fanout: int = 1, seed: Optional[int] = None) -> "NSVectorEnv":
+        """Batched ``get_planning_env()``: a new batch whose lanes ``r * fanout + k`` are copies of
+        env ``r`` (state, episode time, list cursors; parameters too when the agent is told about
+        them -- ``delta_change_notification`` or a copy of a copy -- else the initial parameters).
+        The copy is a simulation env (``is_sim_env``): with ``in_sim_change`` False its parameters
+        are frozen and notifications muted.  ``fanout`` > 1 gives every root ``fanout`` lanes for
+        Monte-Carlo rollouts (``rollout``), the device-side form of MCTS's per-simulation deepcopy
+        (``benchmark_algorithms/MCTS.py:130-131``).  Philox streams are re-keyed (``seed``), as the
+        reference reseeds the copy's generators."""
+        assert self.has_reset, "The environment must be reset before getting the planning environment."
+        c = self._ctor
+        kw = dict(c["env_kwargs"])
+        # the copy sits in the gym.make chain __deepcopy__ builds: registered TimeLimit for classic
+        # control, FrozenLake-v1's 100, max_episode_steps=1000 for CliffWalking / Bridge
+        kw.pop("max_episode_steps", None)
+        limit = self._PLANNING_LIMIT.get(self.program.env_kind)
+        if limit is not None:
+            kw["max_episode_steps"] = limit
+        rows, tp = c["rows"], c["tunable_params"]
+        if rows is not None:
+            if rows is True:                          # one dict per env -> repeat the dicts
+                tp = [d for d in tp for _ in range(fanout)]
+            else:
+                rows = np.repeat(self.rows, fanout, axis=0)
+        if seed is None:
+            seed = (int(self.program.spec.seed) * 0x9E3779B97F4A7C15 + int(self.lib.nsgym_step_index(self._h)) + 1) \
+                & (2**64 - 1)
+        plan = type(self).__new__(type(self))
+        NSVectorEnv.__init__(
+            plan, c["env_id"], tp, self.num_envs * fanout, change_notification=c["change_notification"],
+            delta_change_notification=c["delta_change_notification"], in_sim_change=c["in_sim_change"],
+            scalar_reward=c["scalar_reward"], persistent_params=c["persistent_params"], precision=c["precision"],
+            autoreset="none", seed=seed, env_id_offset=0, device=self.device, want_obs=c["want_obs"],
+            want_delta=c["want_delta"], rows=rows, pools=c["pools"], **kw)
+        theta_from_init = not (self.is_sim_env or self.delta_change_notification)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_fanout(self._h, plan._h, int(fanout), int(theta_from_init), self._stream()),
+                     "nsgym_fanout")
+        plan.lib.nsgym_set_step_index(plan._h, int(self.lib.nsgym_step_index(self._h)))
+        plan.is_sim_env = True
+        plan.has_reset = True
+        plan.fanout = fanout
+        return plan
+
+    def snapshot(self):
+        """Device copy of everything a step mutates; ``restore`` rewinds the batch to it."""
+        buf = torch.empty(int(self.lib.nsgym_snapshot_bytes(self._h)), dtype=torch.uint8, device=self.device)
+        idx = C.c_uint64(0)
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_snapshot(self._h, _ptr(buf), C.byref(idx), self._stream()), "nsgym_snapshot")
+        return buf, int(idx.value)
+
+    def restore(self, snap):
+        buf, idx = snap
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_restore(self._h, _ptr(buf), idx, self._stream()), "nsgym_restore")
 
     # ---- notification control (base.py:443-458) ----
     def freeze(self, mode: bool = True):

@@ -82,6 +82,23 @@ def port_envs(case: dict, n_envs: int, env_streams=None, namespaces=None):
     return envs
 
 
+def planning_envs(envs, env_streams=None):
+    """``get_planning_env()`` of every env (reference wrappers or ports).  The reference reseeds
+    the copy's generators with fresh entropy (``_reseed_planning_env_rngs``) and builds a new base
+    env; under injection both are pointed back at the env's pre-drawn tables."""
+    plans = []
+    for i, e in enumerate(envs):
+        p = e.get_planning_env()
+        if env_streams is not None and not isinstance(p, NSEnvPort):
+            st = env_streams[i]
+            for slot, fn in enumerate(p.tunable_params.values()):
+                if hasattr(fn, "rng"):
+                    fn.rng = S_.SlotRng(st, slot)
+            p.unwrapped.np_random = S_.EnvNpRandom(st)
+        plans.append(p)
+    return plans
+
+
 def draw_actions(case: dict, seed: int, n_steps: int, n_envs: int):
     """Actions [K, N] (int64) or [K, N, 1] float64 for Box action spaces."""
     rng = np.random.default_rng(seed)

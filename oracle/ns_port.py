@@ -491,6 +491,13 @@ class NSEnvPort:
                  terminal_cliff=False, max_episode_steps=None, streams=None, **make_kwargs):
         if delta_change_notification:               # base.py:252-255
             assert change_notification
+        self._ctor = dict(env_id=env_id, tunable_params=tunable_params, change_notification=change_notification,
+                          delta_change_notification=delta_change_notification, in_sim_change=in_sim_change,
+                          scalar_reward=scalar_reward, persistent_params=persistent_params,
+                          initial_prob_dist=initial_prob_dist, modified_rewards=modified_rewards,
+                          terminal_cliff=terminal_cliff, max_episode_steps=max_episode_steps, streams=streams,
+                          **make_kwargs)
+        self.has_reset = False
         if env_id in ("ns_gym/Bridge-v0", "Bridge"):
             env_id = "ns_gym_port/Bridge-v0"
         if "FrozenLake" in env_id:
@@ -681,6 +688,7 @@ class NSEnvPort:
     # ---- reset --------------------------------------------------------------------------
     def reset(self, *, seed=None, options=None):
         state, info = self.env.reset(seed=seed, options=options)   # base.py:377
+        self.has_reset = True
         self.t = 0
         if not self.persistent_params:               # base.py:381-391
             old = self.states
@@ -721,6 +729,59 @@ class NSEnvPort:
         for child, k in zip(children, self.keys):
             if self.states[k].fn_rng is not None:
                 self.states[k].fn_rng = np.random.default_rng(seed=child)
+
+    # ---- planning copies -----------------------------------------------------------------
+    _PLAN_LIMIT = {"FrozenLakeEnv": 100, "CliffWalkingEnv": 1000, "BridgePort": 1000}
+
+    def _deepcopy(self):
+        """``__deepcopy__`` of the reference wrappers (classic_control.py:137-186, toy_text.py:
+        220-251, 483-511, 684-711): a NEW gym.make chain (fresh TimeLimit count, registered limit /
+        100 / 1000), reset, then state, t, current parameters and update-function state copied in."""
+        c = dict(self._ctor)
+        c["max_episode_steps"] = self._PLAN_LIMIT.get(self.name)       # None: registered limit
+        sim = NSEnvPort(**c)
+        sim.env.reset()
+        sim.has_reset = True
+        sim.states = copy.deepcopy(self.states)          # cursors, Memoryless times (rngs: see harness)
+        sim.t = copy.deepcopy(self.t)
+        if self.name in _CLASSIC:
+            sim.base.state = copy.deepcopy(self.base.state)
+            for k in self.keys:
+                setattr(sim.base, k, copy.deepcopy(getattr(self.base, k)))
+            resolve_dependencies(self.name, sim.base)
+        elif self.name == "BridgePort":
+            sim.base.s = copy.deepcopy(self.base.s)
+            if self.split:
+                sim.base.P_left, sim.base.P_right = list(self.base.P_left), list(self.base.P_right)
+            else:
+                sim.base.P = list(self.base.P)
+        else:
+            sim.base.s = copy.deepcopy(self.base.s)
+            sim.transition_prob = copy.deepcopy(self.transition_prob)
+            sim.table_prob = list(self.table_prob)
+        sim.is_sim_env = True
+        return sim
+
+    def get_planning_env(self):
+        """classic_control.py:120-135, toy_text.py:212-218, 471-481, 669-682."""
+        assert self.has_reset, "The environment must be reset before getting the planning environment."
+        plan = self._deepcopy()
+        if not (self.is_sim_env or self.delta_change_notification):
+            if self.name in _CLASSIC:
+                # NOTE no _dependency_resolver here (classic_control.py:131-135): CartPole's total_mass /
+                # polemass_length keep the values derived from the TRUE parameters until a step of a
+                # copy with in_sim_change True recomputes them
+                for k, v in self.initial.items():
+                    setattr(plan.base, k, copy.deepcopy(v))
+            elif self.name == "BridgePort":
+                if self.split:
+                    plan.base.P_left, plan.base.P_right = list(self.init_left), list(self.init_right)
+                else:
+                    plan.base.P = list(self.init_uniform)
+            else:
+                plan.transition_prob = copy.deepcopy(self.initial_prob_dist)
+                plan.table_prob = list(self.initial_prob_dist)
+        return plan
 
     # ---- introspection used by the tests ---------------------------------------------------
     def theta(self) -> dict:

@@ -65,7 +65,8 @@ def _raw_state_of(env):
 
 
 class SyncVector:
-    def __init__(self, envs, env_streams=None, clock=None):
+    def __init__(self, envs, env_streams=None, clock=None, autoreset=True):
+        self.autoreset = autoreset          # False: single-env semantics, stepping past an end allowed
         self.envs = list(envs)
         self.n = len(self.envs)
         self.env_streams = env_streams
@@ -108,19 +109,22 @@ class SyncVector:
                         a = a.item()
                     obs, r, term, trunc, info = e.step(a)
                     outs.append((obs, r, term, trunc, info, False))
-        self.needs_reset = np.array([o[2] or o[3] for o in outs])
+        self.needs_reset = np.array([(o[2] or o[3]) and self.autoreset for o in outs])
         return outs
 
 
-def trace(vec: SyncVector, actions, first_row=1):
+def trace(vec: SyncVector, actions, first_row=1, do_reset=True):
     """Run ``len(actions)`` vector steps after an initial reset (table row 0) and record
-    arrays [K, N, ...].  ``actions`` is [K, N] (or [K, N, A] for Box actions)."""
+    arrays [K, N, ...].  ``actions`` is [K, N] (or [K, N, A] for Box actions).
+    ``do_reset=False`` continues from the envs' current state (planning copies)."""
     K, N = len(actions), vec.n
     keys = vec.keys
-    r0 = vec.reset(k=0)
-    rec = {
-        "obs0": np.stack([np.asarray(o[0]["state"]) for o in r0]),
-        "raw0": np.stack([_raw_state_of(e) for e in vec.envs]),
+    rec = {}
+    if do_reset:
+        r0 = vec.reset(k=0)
+        rec["obs0"] = np.stack([np.asarray(o[0]["state"]) for o in r0])
+        rec["raw0"] = np.stack([_raw_state_of(e) for e in vec.envs])
+    rec.update({
         "reward": np.zeros((K, N)),
         "terminated": np.zeros((K, N), dtype=bool),
         "truncated": np.zeros((K, N), dtype=bool),
@@ -130,7 +134,7 @@ def trace(vec: SyncVector, actions, first_row=1):
         "delta_change": np.zeros((K, N, len(keys))),
         "gt_change": np.zeros((K, N, len(keys)), dtype=np.int64),
         "gt_delta": np.zeros((K, N, len(keys))),
-    }
+    })
     obs_l, raw_l, theta_l = [], [], []
     for k in range(K):
         outs = vec.step(actions[k], k=first_row + k)

@@ -25,10 +25,33 @@ N_ENVS = 4
 SEED = 101
 
 
+def planning(out_dir, only):
+    """tests/golden/planning/<scenario>.npz: traces of the reference's get_planning_env() copies."""
+    import warnings
+
+    from tests import parity_util as pu
+    from tests.planning_cases import PLAN_CASES
+
+    os.makedirs(os.path.join(out_dir, "planning"), exist_ok=True)
+    for name, sc in sorted(PLAN_CASES.items()):
+        if only and name not in only:
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr0, tr1, (actions, u, z) = pu.oracle_planning_trace(harness.reference_envs, sc, N_ENVS, SEED)
+        tr1 = {k: (v.astype(np.int8) if v.dtype == bool else v) for k, v in tr1.items()}
+        np.savez_compressed(os.path.join(out_dir, "planning", f"{name}.npz"), actions=actions, uniforms=u, normals=z,
+                            **tr1)
+        print(f"planning/{name}: k0={sc['k0']} k1={sc['k1']} ended={int(tr1['terminated'].sum() + tr1['truncated'].sum())}")
+
+
 def main():
     assert ref_loader.available(), "the reference tree is needed to (re)generate golden vectors"
     out_dir = os.path.dirname(os.path.abspath(__file__))
     only = set(sys.argv[1:])
+    if "--planning" in only:
+        only.discard("--planning")
+        return planning(out_dir, only)
     for name, case in sorted(CASES.items()):
         if only and name not in only:
             continue

@@ -27,27 +27,32 @@ def oracle_trace(case, n_envs, seed, steps=None, actions=None):
     return tr, actions, u, z
 
 
-def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_step"):
-    """Same trace from the CUDA path with the same injected tables."""
-    import torch
-
+def gpu_env(case, n_envs, precision="fp64", autoreset="next_step"):
+    """The case's batch on the CUDA path (heterogeneous cases: one tunable_params dict per env)."""
     import ns_gym_b200.schedulers as PS
     import ns_gym_b200.update_functions as PU
     from ns_gym_b200.vector_env import NSVectorEnv
-    from ns_gym_b200 import native as nv
 
     kw = dict(precision=precision, autoreset=autoreset, want_delta=True, want_obs=True,
               **case.get("wrapper", {}), **case.get("make", {}))
-    if "params_of" in case:       # heterogeneous batch: one tunable_params dict per env (nsgym_create_rows)
-        env = NSVectorEnv.heterogeneous(case["env_id"], [case["params_of"](PS, PU, e) for e in range(n_envs)], **kw)
-    else:
-        env = NSVectorEnv(case["env_id"], case["params"](PS, PU), n_envs, **kw)
+    if "params_of" in case:       # heterogeneous batch (nsgym_create_rows)
+        return NSVectorEnv.heterogeneous(case["env_id"], [case["params_of"](PS, PU, e) for e in range(n_envs)], **kw)
+    return NSVectorEnv(case["env_id"], case["params"](PS, PU), n_envs, **kw)
+
+
+def gpu_run(env, actions, u, z, first_row=1, do_reset=True):
+    """Drive ``env`` with the injected tables (row 0: reset draws, row first_row + k: step k) and
+    record the same trace as ``oracle.vector.trace``."""
+    import torch
+
+    from ns_gym_b200 import native as nv
+
+    n_envs = env.num_envs
     dev = env.device
     U = torch.as_tensor(u, dtype=torch.float64, device=dev).contiguous()
     Z = torch.as_tensor(z, dtype=torch.float64, device=dev).contiguous()
     K = len(actions)
     keys = env.keys
-    D = env.program.n_dist if env.program.is_grid else 1
 
     def raw_state():
         s = env.buffers["state"]
@@ -57,13 +62,17 @@ def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_ste
         o = env.observation()
         return o.cpu().numpy() if not env.program.is_grid else o.cpu().numpy().astype(np.int64)
 
-    env.reset(inject_uniform=U[0])
-    rec = {"obs0": obs_state(), "raw0": raw_state()}
+    rec = {}
+    if do_reset:
+        env.reset(inject_uniform=U[0])
+        rec = {"obs0": obs_state(), "raw0": raw_state()}
     lists = {k: [] for k in ("obs", "raw", "theta", "reward", "terminated", "truncated", "was_reset",
                              "relative_time", "env_change", "delta_change", "gt_change", "gt_delta")}
+    bad = False
     for k in range(K):
         a = torch.as_tensor(np.asarray(actions[k]).reshape(n_envs))
-        obs, reward, term, trunc, info = env.step(a, inject_uniform=U[k + 1], inject_normal=Z[k + 1])
+        obs, reward, term, trunc, info = env.step(a, inject_uniform=U[first_row + k], inject_normal=Z[first_row + k])
+        bad |= bool((env.buffers["flags"] & nv.FLAG_BAD_DIST).any().item())
         lists["obs"].append(obs_state())
         lists["raw"].append(raw_state())
         th = env.theta()
@@ -83,9 +92,41 @@ def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_ste
         lists["gt_delta"].append(np.stack([info["Ground Truth Delta Change"][q].double().cpu().numpy() for q in keys], 1))
     for k2, v in lists.items():
         rec[k2] = np.stack(v)
-    rec["_bad_dist"] = bool((env.buffers["flags"] & nv.FLAG_BAD_DIST).any().item())
-    del D
+    rec["_bad_dist"] = bad
     return rec
+
+
+def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_step"):
+    """Same trace from the CUDA path with the same injected tables."""
+    return gpu_run(gpu_env(case, n_envs, precision, autoreset), actions, u, z)
+
+
+# ---- planning copies (tests/planning_cases.py) ----
+def oracle_planning_trace(builder, sc, n_envs, seed, tables=None):
+    """(trace of the roots over k0 steps, trace of their planning copies over k1 steps, inputs)."""
+    case, k0, k1 = sc["case"], sc["k0"], sc["k1"]
+    if tables is None:
+        actions = harness.draw_actions(case, seed + 1, k0 + k1, n_envs)
+        u, z = harness.S_.draw_tables(seed, n_envs, k0 + k1 + 1, n_slots_of(case))
+    else:
+        actions, u, z = tables
+    clock = harness.S_.Clock()
+    per_env = [harness.S_.EnvStreams(u[:, :, i], z[:, :, i], clock) for i in range(n_envs)]
+    envs = builder(case, n_envs, per_env)
+    tr0 = vector.trace(vector.SyncVector(envs, per_env, clock), actions[:k0])
+    plans = harness.planning_envs(envs, per_env)
+    tr1 = vector.trace(vector.SyncVector(plans, per_env, clock, autoreset=False), actions[k0:],
+                       first_row=k0 + 1, do_reset=False)
+    return tr0, tr1, (actions, u, z)
+
+
+def gpu_planning_trace(sc, n_envs, actions, u, z, precision="fp64"):
+    case, k0 = sc["case"], sc["k0"]
+    env = gpu_env(case, n_envs, precision)
+    tr0 = gpu_run(env, actions[:k0], u, z)
+    plan = env.get_planning_env()
+    tr1 = gpu_run(plan, actions[k0:], u, z, first_row=k0 + 1, do_reset=False)
+    return tr0, tr1
 
 
 def compare(ref, got, rtol=FP64_RTOL, atol=FP64_ATOL, float_obs_rtol=None, name=""):

@@ -32,3 +32,30 @@ def test_port_matches_golden(name):
         want = g[key]
         assert np.array_equal(np.asarray(got).astype(want.dtype) if want.dtype.kind in "iu" else got, want,
                               equal_nan=got.dtype.kind == "f"), f"{name}: {key} differs from golden"
+
+
+# ---- planning copies ------------------------------------------------------------------------------
+from tests import parity_util as pu  # noqa: E402
+from tests.planning_cases import PLAN_CASES  # noqa: E402
+
+PLAN_NAMES = sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLDEN, "planning", "*.npz")))
+
+
+def test_every_planning_case_has_a_golden_file():
+    assert set(PLAN_NAMES) == set(PLAN_CASES)
+
+
+@pytest.mark.parametrize("name", PLAN_NAMES)
+def test_port_planning_copies_match_golden(name):
+    import warnings
+
+    g = np.load(os.path.join(GOLDEN, "planning", f"{name}.npz"))
+    n = g["uniforms"].shape[2]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, tr, _ = pu.oracle_planning_trace(harness.port_envs, PLAN_CASES[name], n, 0,
+                                            tables=(g["actions"], g["uniforms"], g["normals"]))
+    for key, got in tr.items():
+        want = g[key]
+        assert np.array_equal(np.asarray(got).astype(want.dtype) if want.dtype.kind in "iu" else got, want,
+                              equal_nan=got.dtype.kind == "f"), f"{name}: {key} differs from golden"

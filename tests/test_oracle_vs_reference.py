@@ -44,3 +44,21 @@ def test_port_matches_reference_bit_for_bit(name):
         assert a.shape == b.shape, key
         assert np.array_equal(a, b, equal_nan=True), (
             f"{name}: {key} differs at {np.argwhere(a != b)[:5]}")
+
+
+# ---- planning copies: get_planning_env() of the reference vs the port -----------------------------
+from tests import parity_util as pu  # noqa: E402
+from tests.planning_cases import PLAN_CASES  # noqa: E402
+
+
+@pytest.mark.parametrize("name", sorted(PLAN_CASES))
+def test_port_planning_copies_match_reference(name):
+    import warnings
+
+    sc = PLAN_CASES[name]
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        _, ref, tables = pu.oracle_planning_trace(harness.reference_envs, sc, N_ENVS, seed=31)
+        _, port, _ = pu.oracle_planning_trace(harness.port_envs, sc, N_ENVS, seed=31, tables=tables)
+    for key in ref:
+        assert np.array_equal(ref[key], port[key], equal_nan=True), f"{name}: {key} differs"
