@@ -115,7 +115,13 @@ enum {
   NSGYM_UPD_D_TARGET = 36,       /* :264-293 uf0 = theta, uf1..4 = target */
   NSGYM_UPD_D_LERP = 37,         /* :296-331 uf0 = T, pool_f[ui0..] = start[D], (end-start)[D] */
   NSGYM_UPD_D_STEPWISE = 38,     /* :100-130 ui1 distributions of D doubles at pool_f[ui0..] */
-  NSGYM_UPD_D_CYCLIC = 39        /* :334-356 */
+  NSGYM_UPD_D_CYCLIC = 39,       /* :334-356 */
+  NSGYM_UPD_D_RANDOM = 40        /* RandomCategorical :11-38: Dirichlet(1,..,1) = standard exponentials
+                                    from the env's Philox stream scaled by the reciprocal of their sum */
+  /* Lipschitz bound (LCBoundedDistrubutionUpdate :133-183) on any distribution opcode: ui[2] = 1,
+   * uf[5] = L; the candidate must satisfy W1(p, p') <= L |t - prev_time| (= L: the rule is called
+   * every step).  D_RANDOM is redrawn until it does (<= 1e5 tries, as the reference); a
+   * deterministic rule that fails sets NSGYM_FLAG_BAD_DIST (the reference raises). */
 };
 
 /* ---- constraint rules (wrappers/classic_control.py:193-422) ---- */

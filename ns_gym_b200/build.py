@@ -53,7 +53,8 @@ def _source_digest() -> str:
             h.update(name.encode())
             with open(path, "rb") as f:
                 h.update(f.read())
-    h.update(repr((ARCH, COMMON, UNITS)).encode())
+    # flags without the absolute include paths: the tree may be mounted elsewhere (GPU box)
+    h.update(repr((ARCH, [c for c in COMMON if c not in (INCLUDE, CSRC)], UNITS)).encode())
     return h.hexdigest()
 
 

@@ -79,7 +79,7 @@ GRID_KINDS = (nv.ENV_FROZENLAKE, nv.ENV_CLIFFWALKING, nv.ENV_BRIDGE)
 
 _STATEFUL_UPDATES = {
     "RandomWalk", "RandomWalkWithDrift", "RandomWalkWithDriftAndTrend", "OrnsteinUhlenbeck",
-    "BoundedRandomWalk", "RandomCategorical", "StepWiseUpdate", "CyclicUpdate",
+    "BoundedRandomWalk", "RandomCategorical", "LCBoundedDistrubutionUpdate", "StepWiseUpdate", "CyclicUpdate",
     "DistributionStepWiseUpdate", "DistributionCyclicUpdate"}
 _STATEFUL_SCHEDS = {"RandomScheduler", "DecayingProbabilityScheduler", "MemorylessScheduler",
                     "CustomScheduler"}
@@ -303,8 +303,25 @@ def _lower_dist_update(fn, slot, pools, planes, j, n_dist):
         flat = [x for d in fn.dist_list for x in check(d)]
         slot.ui[0], slot.ui[1] = pools.add_f(flat), len(fn.dist_list)
         _need_plane(slot, planes, j)
-    elif kind in ("RandomCategorical", "LCBoundedDistrubutionUpdate", "BudgetBoundedIncrement"):
-        raise CompileError(f"{kind} is not lowered to the device yet (SURVEY 8(f) rank 4)")
+    elif kind == "RandomCategorical":
+        slot.upd_op = nv.UPD_D_RANDOM
+    elif kind == "LCBoundedDistrubutionUpdate":
+        # distribution.py:155-164: the inner rule is built as update_fn(scheduler), so only rules whose
+        # constructor takes the scheduler alone can be inner rules at all
+        inner = getattr(fn, "update_fn", None)
+        name = "RandomCategorical" if inner is None else (
+            inner.__name__ if isinstance(inner, type) else type(inner).__name__)
+        if name == "RandomCategorical":
+            slot.upd_op = nv.UPD_D_RANDOM
+        elif name == "DistributionNoUpdate":
+            slot.upd_op = nv.UPD_D_NOP
+        else:
+            raise CompileError(f"LCBoundedDistrubutionUpdate around {name} cannot be compiled")
+        slot.ui[2] = 1
+        uf[5] = float(fn.L)
+    elif kind == "BudgetBoundedIncrement":
+        raise CompileError(f"{kind} is broken upstream (its __call__ unpacks a 3-tuple into 2 names) and is "
+                           "not lowered")
     else:
         raise CompileError(f"update function {kind} cannot drive a slip distribution")
 
@@ -381,6 +398,9 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
         f"Tunable parameters {list(tunable_params.keys())} not all in default tunable parameters "
         f"{list(TUNABLE_PARAMS.get(env_class, {}).keys())} for environment {env_class}")
     _check_aliasing(tunable_params)
+    if persistent_params and any(type(f).__name__ == "LCBoundedDistrubutionUpdate" for f in tunable_params.values()):
+        raise CompileError("LCBoundedDistrubutionUpdate with persistent_params: the bound L |t - prev_time| "
+                           "carries prev_time across resets in the reference; not lowered")
     is_grid = kind in GRID_KINDS
     spec = nv.NsgymSpec()
     spec.abi_version = nv.ABI_VERSION

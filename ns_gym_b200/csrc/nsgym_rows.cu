@@ -47,6 +47,11 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
                  "from spec->slots[%d] (the key set is shared by the batch)", (long long)e, j, j);
         return -1;
       }
+      if (a.ui[2] != key.ui[2] || a.uf[5] != key.uf[5]) {
+        snprintf(err, err_len, "row (env %lld, slot %d): the Lipschitz bound (ui[2], uf[5]) is shared by the batch",
+                 (long long)e, j);
+        return -1;
+      }
       if (int rc = validate_row_slot(&spec, &a, j, err, err_len)) return rc;
       lower_row<R>(spec, a, j, iw, rw, dw);
       uint32_t m = 0;

@@ -28,7 +28,7 @@ SCHED_WINDOW, SCHED_RANDOM, SCHED_DECAY, SCHED_MEMORYLESS = 4, 5, 6, 7
 UPD_NOP, UPD_ADD, UPD_ADD_T, UPD_POLY, UPD_MUL, UPD_MUL_EXP, UPD_ADD_SIN = 0, 1, 2, 3, 4, 5, 6
 UPD_SIGMOID, UPD_LERP, UPD_STEPWISE, UPD_CYCLIC, UPD_RW, UPD_OU, UPD_BRW = 7, 8, 9, 10, 11, 12, 13
 UPD_D_NOP, UPD_D_INC, UPD_D_DEC, UPD_D_UNIFORM = 32, 33, 34, 35
-UPD_D_TARGET, UPD_D_LERP, UPD_D_STEPWISE, UPD_D_CYCLIC = 36, 37, 38, 39
+UPD_D_TARGET, UPD_D_LERP, UPD_D_STEPWISE, UPD_D_CYCLIC, UPD_D_RANDOM = 36, 37, 38, 39, 40
 
 CONS_NONE, CONS_REJECT_LE0, CONS_REJECT_LT0, CONS_ACRO_LENGTH1, CONS_ACRO_COM = 0, 1, 2, 3, 4
 

@@ -79,16 +79,31 @@ class DistributionLinearInterpolation(base.UpdateDistributionFn):
 
 
 class RandomCategorical(base.UpdateDistributionFn):
-    """Fresh ``Dirichlet(1)`` draw per fire (``distribution.py:11-38``).  SURVEY 8(f) rank 4:
-    not yet lowered to the device -- the compiler rejects it."""
+    """Fresh ``Dirichlet(1, .., 1)`` draw per fire (``distribution.py:11-38``).  On the device:
+    standard exponentials from the env's Philox stream, scaled by the reciprocal of their sum."""
 
     def __init__(self, scheduler, seed: Optional[int] = None) -> None:
         super().__init__(scheduler)
         self.seed = seed
 
 
+class LCBoundedDistrubutionUpdate(base.UpdateDistributionFn):
+    """Redraws the inner rule until ``W1(p, p') <= L * |t - prev_time|`` (``distribution.py:133-183``;
+    the class name keeps the reference's spelling).  The inner rule defaults to
+    ``RandomCategorical``, the only one that is redrawn on the device (a deterministic inner rule
+    either passes at once or can never pass: the reference raises, the device flags it)."""
+
+    def __init__(self, scheduler, L: float, update_fn=None) -> None:
+        super().__init__(scheduler)
+        self.L = L
+        if update_fn is not None:
+            assert isinstance(update_fn, type) and issubclass(update_fn, base.UpdateDistributionFn), (
+                "update_fn must be a subclass of base.UpdateDistributionFn")
+        self.update_fn = update_fn
+
+
 __all__ = [
     "DistributionCyclicUpdate", "DistributionDecrementUpdate", "DistributionIncrementUpdate",
     "DistributionLinearInterpolation", "DistributionNoUpdate", "DistributionStepWiseUpdate",
-    "RandomCategorical", "TargetReversion", "UniformDrift",
+    "LCBoundedDistrubutionUpdate", "RandomCategorical", "TargetReversion", "UniformDrift",
 ]

@@ -25,6 +25,9 @@ def _inject(tunable_params: dict, st: S_.EnvStreams):
             fn.rng = S_.SlotRng(st, slot)
         if hasattr(fn.scheduler, "rng"):
             fn.scheduler.rng = S_.SlotRng(st, slot)
+        inner = getattr(fn, "update_fn", None)          # LCBoundedDistrubutionUpdate's inner RandomCategorical
+        if inner is not None and hasattr(inner, "rng"):
+            inner.rng = S_.SlotRng(st, slot)
 
 
 def make_streams(seed, n_envs, n_rows, n_slots):
@@ -94,6 +97,9 @@ def planning_envs(envs, env_streams=None):
             for slot, fn in enumerate(p.tunable_params.values()):
                 if hasattr(fn, "rng"):
                     fn.rng = S_.SlotRng(st, slot)
+                inner = getattr(fn, "update_fn", None)
+                if inner is not None and hasattr(inner, "rng"):
+                    inner.rng = S_.SlotRng(st, slot)
             p.unwrapped.np_random = S_.EnvNpRandom(st)
         plans.append(p)
     return plans

@@ -72,11 +72,12 @@ _UPD_ATTRS = {
     "TargetReversion": ("target", "theta"),
     "DistributionLinearInterpolation": ("start_dist", "end_dist", "T"),
     "RandomCategorical": (),
+    "LCBoundedDistrubutionUpdate": ("L",),
 }
 
 STOCHASTIC_UPDATES = {
     "RandomWalk", "RandomWalkWithDrift", "RandomWalkWithDriftAndTrend",
-    "OrnsteinUhlenbeck", "BoundedRandomWalk", "RandomCategorical",
+    "OrnsteinUhlenbeck", "BoundedRandomWalk", "RandomCategorical", "LCBoundedDistrubutionUpdate",
 }
 STOCHASTIC_SCHEDS = {"RandomScheduler", "DecayingProbabilityScheduler", "MemorylessScheduler"}
 
@@ -123,6 +124,14 @@ def describe(fn) -> dict:
     for a in _UPD_ATTRS[kind]:
         d[a] = copy.deepcopy(getattr(fn, a))
     d["rng"] = _rng_of(fn, kind in STOCHASTIC_UPDATES)
+    if kind == "LCBoundedDistrubutionUpdate":       # distribution.py:155-164: inner rule, default RandomCategorical
+        inner = getattr(fn, "update_fn", None)      # instance (reference) | class or None (descriptions)
+        name = "RandomCategorical" if inner is None else (
+            inner.__name__ if isinstance(inner, type) else type(inner).__name__)
+        if name != "RandomCategorical":
+            raise TypeError("oracle: LCBoundedDistrubutionUpdate is restated for its default inner rule only")
+        d["inner"] = {"kind": "RandomCategorical"}
+        d["rng"] = copy.deepcopy(inner.rng) if hasattr(inner, "rng") else np.random.default_rng()
     sch = fn.scheduler
     skind = type(sch).__name__
     if skind not in _SCHED_ATTRS:
@@ -314,10 +323,19 @@ def apply_update(d: dict, st: SlotState, param, t, streams, slot):
     if k == "DistributionLinearInterpolation":      # :326-331
         frac = min(t / d["T"], 1.0)
         return [s + (e - s) * frac for s, e in zip(d["start_dist"], d["end_dist"])]
-    if k == "RandomCategorical":                    # :37-38 (numpy-RNG mode only)
+    if k == "RandomCategorical":                    # :37-38
         if streams is not None:
-            raise NotImplementedError("RandomCategorical has no injected-stream convention")
+            return streams.dirichlet(slot, len(param))
         return list(st.fn_rng.dirichlet(np.ones(len(param))))
+    if k == "LCBoundedDistrubutionUpdate":          # :166-183 rejection loop around the inner rule
+        inner = d["inner"]
+        cur = np.asarray(param, dtype=float)
+        bound = d["L"] * abs(t - st.prev_time)
+        for _ in range(int(1e5)):
+            cand = apply_update(inner, st, list(param), t, streams, slot)
+            if w1_index_distance(cur, np.asarray(cand, dtype=float)) <= bound:
+                return cand
+        raise ValueError("Could not find a Lipschitz-continuous update")
     raise TypeError(k)
 
 

@@ -18,7 +18,13 @@ The CUDA kernel uses exactly the same addressing (``include/nsgym_b200.h``):
     uniforms[k][lane][env]   lane 0          gridworld draw (slip; start-cell draw on reset)
                              lane 1..4       classic-control reset draws (initial state)
                              lane 5+j        scheduler draw of parameter slot j
+                             lane 5+P+(j*16+r)*4+i  i-th uniform of the r-th Dirichlet draw (r mod 16) of
+                                                   parameter slot j at this step (RandomCategorical; the
+                                                   Lipschitz-bounded wrapper redraws until accepted)
     normals [k][j][env]      update-function standard normal of parameter slot j
+
+Dirichlet(1, .., 1) convention under injection (numpy draws standard gammas and scales by the
+reciprocal of their sum): e_i = -log1p(-u_i), p_i = e_i * (1 / (e_0 + .. + e_{n-1})).
 
 ``Generator.normal(mu, sigma)`` equals ``mu + sigma * standard_normal()`` bit for bit, so
 feeding standard normals reproduces the reference arithmetic exactly.
@@ -33,8 +39,26 @@ N_RESET_LANES = 4
 LANE_SCHED0 = LANE_RESET0 + N_RESET_LANES  # 5
 
 
+DIR_TRIES = 16         # injected Dirichlet draws available per (step, slot); further tries wrap around
+DIR_WIDTH = 4          # uniforms per draw (3 or 4 outcomes)
+
+
 def n_uniform_lanes(n_slots: int) -> int:
-    return LANE_SCHED0 + n_slots
+    return LANE_SCHED0 + n_slots + n_slots * DIR_TRIES * DIR_WIDTH
+
+
+def dirichlet_lane(n_slots: int, slot: int, attempt: int, i: int) -> int:
+    return LANE_SCHED0 + n_slots + (slot * DIR_TRIES + attempt % DIR_TRIES) * DIR_WIDTH + i
+
+
+def dirichlet_from_uniforms(us):
+    """Dirichlet(1,..,1) from uniforms: standard exponentials scaled by the reciprocal of their sum."""
+    e = [-np.log1p(-u) for u in us]
+    acc = 0.0
+    for v in e:
+        acc = acc + v
+    inv = 1.0 / acc
+    return [float(v * inv) for v in e]
 
 
 class Clock:
@@ -54,6 +78,8 @@ class EnvStreams:
         self.u = np.asarray(uniforms, dtype=np.float64)
         self.z = np.asarray(normals, dtype=np.float64)
         self.clock = clock
+        self.n_slots = self.z.shape[1]        # lanes of the Dirichlet block start after the scheduler lanes
+        self._dir_seen = {}                   # (k, slot) -> draws made so far at this step
 
     def __deepcopy__(self, memo):
         return self
@@ -63,6 +89,14 @@ class EnvStreams:
 
     def std_normal(self, slot: int) -> float:
         return float(self.z[self.clock.k, slot])
+
+    def dirichlet(self, slot: int, n: int):
+        """The next Dirichlet(1,..,1) draw of parameter slot ``slot`` at the current step."""
+        key = (self.clock.k, slot)
+        attempt = self._dir_seen.get(key, 0)
+        self._dir_seen = {key: attempt + 1} if key not in self._dir_seen else {**self._dir_seen, key: attempt + 1}
+        us = [self.u[self.clock.k, dirichlet_lane(self.n_slots, slot, attempt, i)] for i in range(n)]
+        return dirichlet_from_uniforms(us)
 
 
 class SlotRng:
@@ -80,6 +114,9 @@ class SlotRng:
 
     def random(self):
         return self.s.uniform(LANE_SCHED0 + self.slot)
+
+    def dirichlet(self, alpha):
+        return np.array(self.s.dirichlet(self.slot, len(alpha)))
 
     def geometric(self, p, size=None):
         # inverse-CDF geometric on {1,2,...}: ceil(log1p(-u)/log1p(-p)); shared convention

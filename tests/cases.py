@@ -340,6 +340,22 @@ CASES = {
         lambda S, U: {"P": U.UniformDrift(S.PeriodicScheduler(3), rate=0.1)},
         wrapper=dict(initial_prob_dist=[0.7, 0.1, 0.1, 0.1], change_notification=True,
                      delta_change_notification=True, terminal_cliff=True), steps=120),
+    # ---- stochastic distribution rules ----------------------------------------
+    "frozenlake4_random_categorical": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.RandomCategorical(S.PeriodicScheduler(3))},
+        wrapper=dict(initial_prob_dist=[0.8, 0.1, 0.1], change_notification=True,
+                     delta_change_notification=True), steps=120),
+    "cliff_random_categorical": _c(
+        "CliffWalking-v1",
+        lambda S, U: {"P": U.RandomCategorical(S.BurstScheduler(1, 4))},
+        wrapper=dict(initial_prob_dist=[0.7, 0.1, 0.1, 0.1], change_notification=True,
+                     delta_change_notification=True), make=dict(max_episode_steps=40), steps=100),
+    "bridge_lipschitz_bounded": _c(
+        "ns_gym/Bridge-v0",
+        lambda S, U: {"P": U.LCBoundedDistrubutionUpdate(S.ContinuousScheduler(), L=0.7)},
+        wrapper=dict(initial_prob_dist=[0.4, 0.3, 0.3], change_notification=True,
+                     delta_change_notification=True), steps=100),
     # ---- C4: heterogeneous batches (per-env rows) ---------------------------------------------------
     "c4_cartpole_rows": _het(
         "CartPole-v1", _c4_cartpole,

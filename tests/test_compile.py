@@ -85,8 +85,14 @@ def test_rejections():
     fn = U.RandomWalk(S.ContinuousScheduler())
     with pytest.raises(CompileError):
         compile_program("CartPole-v1", {"gravity": fn, "length": fn}, 4)   # shared stateful object (S13)
-    with pytest.raises(CompileError):
-        compile_program("FrozenLake-v1", {"P": U.RandomCategorical(S.ContinuousScheduler())}, 4)
+    with pytest.raises(CompileError):     # prev_time would carry across resets
+        compile_program("FrozenLake-v1", {"P": U.LCBoundedDistrubutionUpdate(S.ContinuousScheduler(), L=0.5)}, 4,
+                        persistent_params=True)
+    with pytest.raises(CompileError):     # only rules constructible from the scheduler alone can be inner rules
+        compile_program("FrozenLake-v1", {"P": U.LCBoundedDistrubutionUpdate(
+            S.ContinuousScheduler(), L=0.5, update_fn=U.UniformDrift)}, 4)
+    p = compile_program("FrozenLake-v1", {"P": U.LCBoundedDistrubutionUpdate(S.ContinuousScheduler(), L=0.5)}, 4)
+    assert p.spec.slots[0].upd_op == nv.UPD_D_RANDOM and p.spec.slots[0].ui[2] == 1 and p.spec.slots[0].uf[5] == 0.5
     with pytest.raises(CompileError):
         compile_program("CartPole-v1", {"gravity": U.UniformDrift(S.ContinuousScheduler(), 0.1)}, 4)
     with pytest.raises(CompileError):
@@ -131,3 +137,53 @@ def test_reference_objects_compile_too():
                 sb.sched_op, sb.upd_op, sb.theta_index, sb.start, sb.end)
             assert list(sa.uf) == list(sb.uf) and list(sa.sf) == list(sb.sf)
             assert list(sa.si) == list(sb.si) and sa.istate_init == sb.istate_init
+
+
+# ---- heterogeneous batches: compile_rows (BASELINE config C4) -----------------------------------
+def test_compile_rows_layout_and_cursor_planes():
+    from ns_gym_b200.compile import compile_rows, rows_dtype
+
+    per_env = [
+        {"masspole": U.IncrementUpdate(S.PeriodicScheduler(2 + e), k=0.1 * (e + 1)),
+         "gravity": (U.StepWiseUpdate(S.ContinuousScheduler(), [1.0 + e, 2.0]) if e % 2
+                     else U.RandomWalk(S.BurstScheduler(1, 3), sigma=0.1 * e))}
+        for e in range(6)]
+    prog, rows = compile_rows("CartPole-v1", per_env, precision="fp64")
+    assert rows.shape == (6, 2) and rows.dtype == rows_dtype()
+    assert rows.dtype.itemsize == nv.C.sizeof(nv.NsgymSlot)
+    assert rows["sched_op"][:, 0].tolist() == [nv.SCHED_PERIODIC] * 6
+    assert rows["si"][:, 0, 0].tolist() == [2, 3, 4, 5, 6, 7]
+    assert np.allclose(rows["uf"][:, 0, 0], [0.1 * (e + 1) for e in range(6)])
+    assert rows["upd_op"][:, 1].tolist() == [nv.UPD_RW, nv.UPD_STEPWISE] * 3
+    # a cursor plane exists for slot 1 because SOME env needs one; rows that do not need it keep -1
+    assert prog.spec.slots[1].istate_plane == 0 and prog.spec.slots[0].istate_plane == -1
+    assert rows["istate_plane"][:, 1].tolist() == [-1, 0] * 3
+    # every env's list lives in the shared pool at its own offset
+    offs = rows["ui"][1::2, 1, 0].tolist()
+    assert len(set(offs)) == 3 and prog.spec.n_pool_f >= 6
+    # shared key set
+    assert (rows["theta_index"] == rows["theta_index"][0]).all()
+    assert (rows["constraint"] == rows["constraint"][0]).all()
+
+
+def test_compile_rows_rejects_mismatched_key_sets():
+    from ns_gym_b200.compile import compile_rows
+
+    a = {"masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)}
+    b = {"gravity": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)}
+    with pytest.raises(CompileError):
+        compile_rows("CartPole-v1", [a, b])
+    with pytest.raises(CompileError):
+        compile_rows("CartPole-v1", [])
+
+
+def test_heterogeneous_cases_compile_per_env():
+    from ns_gym_b200.compile import compile_rows
+
+    for name, c in CASES.items():
+        if "params_of" not in c:
+            continue
+        prog, rows = compile_rows(c["env_id"], [c["params_of"](S, U, e) for e in range(12)],
+                                  precision="fp64", **c["wrapper"], **c["make"])
+        assert rows.shape == (12, prog.spec.n_slots)
+        assert len({tuple(r) for r in rows["upd_op"].tolist()}) > 1, f"{name}: rows are all alike"
