@@ -455,7 +455,8 @@ def run_gpu(args):
         with open(tpath) as f:
             traffic = json.load(f).get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per step (ncu --set full, profiles/traffic.json)",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": bytes_per_launch_env / per_launch,
                 "kernel_us_per_launch": launch_s * 1e6 / len(shards)}
     if len(shards) > 1:

@@ -59,11 +59,22 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     }
     return cudaGetLastError();
   }
+  // lean instantiation when every bound rule is deterministic
+  bool slow = false;
+  for (int j = 0; j < spec.n_slots; ++j) {
+    const NsgymSlot& sl = spec.slots[j];
+    slow |= sl.sched_op == NSGYM_SCHED_RANDOM || sl.sched_op == NSGYM_SCHED_DECAY ||
+            sl.sched_op == NSGYM_SCHED_MEMORYLESS || sl.upd_op == NSGYM_UPD_D_RANDOM || sl.ui[2] != 0;
+  }
   switch (op) {
-    case OP_STEP: grid_step_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
+    case OP_STEP:
+      if (slow) grid_step_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, io);
+      else grid_step_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, io);
+      break;
     case OP_RESET: grid_reset_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
     case OP_ROLLOUT:
-      grid_rollout_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io, a.k_steps, a.gamma, a.ret, a.len);
+      if (slow) grid_rollout_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, io, a.k_steps, a.gamma, a.ret, a.len);
+      else grid_rollout_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, io, a.k_steps, a.gamma, a.ret, a.len);
       break;
   }
   return cudaGetLastError();

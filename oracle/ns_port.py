@@ -748,6 +748,61 @@ class NSEnvPort:
             if self.states[k].fn_rng is not None:
                 self.states[k].fn_rng = np.random.default_rng(seed=child)
 
+    # ---- transition tables ---------------------------------------------------------------
+    def transition_table(self):
+        """The table the base env samples from right now, as arrays ``prob / next / reward / done``
+        of shape [S, A, D] (outcome k of action a in cell s; unused outcomes of single-outcome rows
+        have prob 0): FrozenLake ``toy_text.py:426-447`` (absorbing G / H rows ``(1.0, s, 0, True)``),
+        CliffWalking ``toy_text.py:86-138`` (no absorbing rows), Bridge ``envs/Bridge.py:189-221``
+        (``transition_matrix``: H / G rows absorbing with the cell's own reward, per-side slip
+        distributions in split mode)."""
+        assert self.name in ("FrozenLakeEnv", "CliffWalkingEnv", "BridgePort")
+        if self.name == "BridgePort":
+            nrow, ncol, D = self.base.nrow, self.base.ncol, 3
+        elif self.name == "FrozenLakeEnv":
+            nrow, ncol, D = self.base.nrow, self.base.ncol, 3
+        else:
+            nrow, ncol, D = 4, 12, 4
+        S = nrow * ncol
+        prob = np.zeros((S, 4, D))
+        nxt = np.zeros((S, 4, D), dtype=np.int64)
+        rew = np.zeros((S, 4, D))
+        done = np.zeros((S, 4, D), dtype=bool)
+        for s in range(S):
+            row, col = divmod(s, ncol)
+            for a in range(4):
+                if self.name == "FrozenLakeEnv":
+                    if bytes(self.base.desc[row, col]) in b"GH":
+                        prob[s, a, 0], nxt[s, a, 0], rew[s, a, 0], done[s, a, 0] = 1.0, s, 0, True
+                        continue
+                    for k, b in enumerate([a, (a + 1) % 4, (a - 1) % 4]):
+                        ns, r, term = self._frozenlake_outcome(s, b)
+                        prob[s, a, k], nxt[s, a, k], rew[s, a, k], done[s, a, k] = self.table_prob[k], ns, r, term
+                elif self.name == "CliffWalkingEnv":
+                    for k, b in enumerate([a, (a + 1) % 4, (a - 1) % 4, (a + 2) % 4]):
+                        ns, r, term = self._cliff_outcome(s, b)
+                        prob[s, a, k], nxt[s, a, k], rew[s, a, k], done[s, a, k] = self.table_prob[k], ns, r, term
+                else:
+                    def cell_reward(r_, c_):             # Bridge.py:159-174
+                        cell = bytes(self.base.map[r_, c_])
+                        return (-1, True) if cell == b"H" else (1, True) if cell == b"G" else (0, False)
+
+                    if bytes(self.base.map[row, col]) in (b"H", b"G"):
+                        r, d = cell_reward(row, col)
+                        prob[s, a, 0], nxt[s, a, 0], rew[s, a, 0], done[s, a, 0] = 1.0, s, r, d
+                        continue
+                    if self.split:
+                        cell_p = self.base.P_left if col < ncol // 2 else self.base.P_right
+                    else:
+                        cell_p = self.base.P
+                    for k, b in enumerate([a, (a + 1) % 4, (a - 1) % 4]):
+                        nr, nc = row + _BRIDGE_DELTA[b][0], col + _BRIDGE_DELTA[b][1]
+                        if not (0 <= nr < nrow and 0 <= nc < ncol):
+                            nr, nc = row, col
+                        r, d = cell_reward(nr, nc)
+                        prob[s, a, k], nxt[s, a, k], rew[s, a, k], done[s, a, k] = cell_p[k], nr * ncol + nc, r, d
+        return {"prob": prob, "next": nxt, "reward": rew, "done": done}
+
     # ---- planning copies -----------------------------------------------------------------
     _PLAN_LIMIT = {"FrozenLakeEnv": 100, "CliffWalkingEnv": 1000, "BridgePort": 1000}
 

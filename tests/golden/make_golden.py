@@ -45,10 +45,31 @@ def planning(out_dir, only):
         print(f"planning/{name}: k0={sc['k0']} k1={sc['k1']} ended={int(tr1['terminated'].sum() + tr1['truncated'].sum())}")
 
 
+def tables(out_dir, only):
+    """tests/golden/tables/<case>.npz: unwrapped.P / transition_matrix of the reference at t = 0..T-1."""
+    import warnings
+
+    from tests import parity_util as pu
+
+    os.makedirs(os.path.join(out_dir, "tables"), exist_ok=True)
+    for name in pu.TABLE_CASES:
+        if only and name not in only:
+            continue
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            tr = pu.oracle_table_trace(harness.reference_envs, CASES[name], 50)
+        np.savez_compressed(os.path.join(out_dir, "tables", f"{name}.npz"), prob=tr["prob"], next=tr["next"],
+                            reward=tr["reward"], done=tr["done"].astype(np.int8))
+        print(f"tables/{name}: {tr['prob'].shape}")
+
+
 def main():
     assert ref_loader.available(), "the reference tree is needed to (re)generate golden vectors"
     out_dir = os.path.dirname(os.path.abspath(__file__))
     only = set(sys.argv[1:])
+    if "--tables" in only:
+        only.discard("--tables")
+        return tables(out_dir, only)
     if "--planning" in only:
         only.discard("--planning")
         return planning(out_dir, only)

@@ -101,6 +101,43 @@ def gpu_trace(case, n_envs, actions, u, z, precision="fp64", autoreset="next_ste
     return gpu_run(gpu_env(case, n_envs, precision, autoreset), actions, u, z)
 
 
+# ---- time-indexed transition tables ----
+TABLE_CASES = ["c2_frozenlake8_drift", "c2_frozenlake8_stepchange", "frozenlake4_ops", "frozenlake8_cyclic_stale",
+               "cliff_terminal", "cliff_drift", "c5_bridge_uniform", "c5_bridge_split", "bridge_stepwise"]
+
+
+def table_of(env):
+    """Current transition table of one env (reference wrapper or port) as arrays [S, A, D]."""
+    if hasattr(env, "transition_table"):
+        return env.transition_table()
+    base = env.unwrapped
+    P = base.transition_matrix if type(base).__name__ == "Bridge" else base.P
+    S, D = len(P), max(len(P[s][a]) for s in P for a in P[s])
+    out = {"prob": np.zeros((S, 4, D)), "next": np.zeros((S, 4, D), dtype=np.int64),
+           "reward": np.zeros((S, 4, D)), "done": np.zeros((S, 4, D), dtype=bool)}
+    for s in range(S):
+        for a in range(4):
+            for k, (p, ns, r, d) in enumerate(P[s][a]):
+                out["prob"][s, a, k], out["next"][s, a, k], out["reward"][s, a, k], out["done"][s, a, k] = p, ns, r, d
+    return out
+
+
+def oracle_table_trace(builder, case, T, seed=3):
+    """Tables in force at NS times 0..T-1 of ONE env stepped from a reset (stepping past episode
+    ends: the parameters keep evolving with t): prob [T, S, A, D] + the time-invariant part."""
+    actions = harness.draw_actions(case, seed + 1, T, 1)
+    clock, per_env, _, _ = harness.make_streams(seed, 1, T + 1, n_slots_of(case))
+    envs = builder(case, 1, per_env)
+    vec = vector.SyncVector(envs, per_env, clock, autoreset=False)
+    vec.reset(k=0)
+    probs, last = [], None
+    for t in range(T):
+        vec.step(actions[t], k=t + 1)
+        last = table_of(envs[0])
+        probs.append(last["prob"])
+    return {"prob": np.stack(probs), "next": last["next"], "reward": last["reward"], "done": last["done"]}
+
+
 # ---- planning copies (tests/planning_cases.py) ----
 def oracle_planning_trace(builder, sc, n_envs, seed, tables=None):
     """(trace of the roots over k0 steps, trace of their planning copies over k1 steps, inputs)."""

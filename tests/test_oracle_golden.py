@@ -59,3 +59,16 @@ def test_port_planning_copies_match_golden(name):
         want = g[key]
         assert np.array_equal(np.asarray(got).astype(want.dtype) if want.dtype.kind in "iu" else got, want,
                               equal_nan=got.dtype.kind == "f"), f"{name}: {key} differs from golden"
+
+
+# ---- transition tables --------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", pu.TABLE_CASES)
+def test_port_transition_tables_match_golden(name):
+    import warnings
+
+    g = np.load(os.path.join(GOLDEN, "tables", f"{name}.npz"))
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        tr = pu.oracle_table_trace(harness.port_envs, CASES[name], g["prob"].shape[0])
+    assert np.array_equal(tr["prob"], g["prob"]) and np.array_equal(tr["next"], g["next"])
+    assert np.array_equal(tr["reward"], g["reward"]) and np.array_equal(tr["done"].astype(np.int8), g["done"])

@@ -62,3 +62,16 @@ def test_port_planning_copies_match_reference(name):
         _, port, _ = pu.oracle_planning_trace(harness.port_envs, sc, N_ENVS, seed=31, tables=tables)
     for key in ref:
         assert np.array_equal(ref[key], port[key], equal_nan=True), f"{name}: {key} differs"
+
+
+# ---- time-indexed transition tables: unwrapped.P / transition_matrix vs the port -------------------
+@pytest.mark.parametrize("name", pu.TABLE_CASES)
+def test_port_transition_tables_match_reference(name):
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        ref = pu.oracle_table_trace(harness.reference_envs, CASES[name], 40)
+        port = pu.oracle_table_trace(harness.port_envs, CASES[name], 40)
+    for key in ref:
+        assert np.array_equal(ref[key], port[key]), f"{name}: {key} differs"
