@@ -269,6 +269,22 @@ size_t nsgym_snapshot_bytes(const NsgymHandle* h);
 int nsgym_snapshot(NsgymHandle* h, void* d_dst, uint64_t* step_index, void* stream);
 int nsgym_restore(NsgymHandle* h, const void* d_src, uint64_t step_index, void* stream);
 
+/* Time-indexed transition table of one gridworld env.
+ * replaces: reading unwrapped.P (NSFrozenLakeWrapper._update_transition_prob_table toy_text.py:
+ * 426-447, NSCliffWalkingWrapper._build_P_from_outcomes :86-138) / Bridge.transition_matrix
+ * (envs/Bridge.py:189-221) after every step of an episode -- the input of value iteration and of
+ * the PAMCTS / RATS-style planners (evaluate/metrics.py:244-297, benchmark_algorithms/rats.py) and
+ * what the unimplemented extract_oracle_transition_table (toy_text.py:513-519) was to return.
+ * For env `env` and NS times t = 0 .. n_times-1 of an episode started by a reset:
+ *   d_prob   double[n_times][S][4][D]  probability of outcome k of action a in cell s at time t
+ *   d_next   int32 [S][4][D], d_reward float[S][4][D], d_done uint8[S][4][D]   (time-invariant)
+ * D = 3 (4 for CliffWalking) outcomes in the reference's order [a, a+1, a-1(, a+2)]; absorbing rows
+ * (FrozenLake G / H, Bridge H / G) have the single outcome (1.0, s, r, True) in k = 0 and zeros
+ * after it.  Deterministic rules give THE table; stochastic rules are sampled from the env's
+ * Philox stream as an episode starting at the handle's current step index would draw them. */
+int nsgym_transition_table(NsgymHandle* h, int64_t env, int n_times, double* d_prob, int32_t* d_next,
+                           float* d_reward, uint8_t* d_done, void* stream);
+
 /* Fire-test + advance stages only (a1 + a2/a3), for known-answer checks of the update
  * functions: applies slot `slot` to d_param (real[N] scalars, or double[D][N]) at times
  * d_time[N]; writes new values in place, d_flag uint8[N], d_delta real[N]. */

@@ -488,6 +488,25 @@ int nsgym_fanout(const NsgymHandle* src, NsgymHandle* dst, int fanout, int theta
   return 0;
 }
 
+int nsgym_transition_table(NsgymHandle* h, int64_t env, int n_times, double* d_prob, int32_t* d_next,
+                           float* d_reward, uint8_t* d_done, void* stream) {
+  if (!h) return fail(-1, "NULL handle");
+  if (!h->grid()) return fail(-1, "transition tables exist for the gridworld kinds only");
+  if (env < 0 || env >= h->spec.n_envs) return fail(-1, "env index out of range");
+  if (n_times <= 0 || n_times > (1 << 20)) return fail(-1, "n_times out of range");
+  if (!d_prob || !d_next || !d_reward || !d_done) return fail(-1, "NULL output");
+  nsg::LaunchIO io{};
+  io.n = h->spec.n_envs; io.count = h->spec.n_envs;
+  io.gid_offset = uint64_t(h->spec.env_id_offset); io.seed = h->spec.seed; io.step_index = h->step_index;
+  io.rows = h->rows.active ? &h->rows : nullptr;
+  io.plan_elapsed = -1;
+  cudaError_t e = nsg::launch_table(h->spec, h->pools, io, env, n_times, d_prob, d_next, d_reward, d_done,
+                                    static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-10, "transition table: %s", cudaGetErrorString(e));
+  h->launches += 2;
+  return 0;
+}
+
 size_t nsgym_snapshot_bytes(const NsgymHandle* h) {
   if (!h) return 0;
   const size_t n = size_t(h->spec.n_envs);

@@ -80,6 +80,46 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   return cudaGetLastError();
 }
 
+template <int KIND, int D, int MAXP>
+static cudaError_t launch_table_k(const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& a, int64_t env,
+                                  int n_times, double* prob, int32_t* next, float* reward, uint8_t* done,
+                                  cudaStream_t stream) {
+  if (spec.n_slots > MAXP || spec.n_dist != D) return cudaErrorInvalidValue;
+  const GridProgram<MAXP> G = build_grid_program<MAXP>(spec, pools);
+  const StepIO<double> io = build_io<double>(a);
+  double* traj = nullptr;
+  cudaError_t e = cudaMallocAsync(reinterpret_cast<void**>(&traj), sizeof(double) * size_t(n_times) * MAXP * D, stream);
+  if (e != cudaSuccess) return e;
+  HetT<double, MAXP> H{};
+  if (a.rows && a.rows->active) {
+    H = build_het_by_index<MAXP>(spec, *a.rows);
+    grid_trajectory_kernel<KIND, D, MAXP, true><<<1, 32, 0, stream>>>(G, H, io, uint32_t(env), n_times, traj);
+  } else {
+    grid_trajectory_kernel<KIND, D, MAXP, false><<<1, 32, 0, stream>>>(G, H, io, uint32_t(env), n_times, traj);
+  }
+  const uint64_t total = uint64_t(n_times) * spec.nrow * spec.ncol * 4;
+  grid_table_kernel<KIND, D, MAXP><<<unsigned((total + 255) / 256), 256, 0, stream>>>(G, traj, n_times, prob, next,
+                                                                                      reward, done);
+  e = cudaGetLastError();
+  cudaFreeAsync(traj, stream);
+  return e;
+}
+
+cudaError_t launch_table(const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& io, int64_t env, int n_times,
+                         double* prob, int32_t* next, float* reward, uint8_t* done, cudaStream_t stream) {
+  switch (spec.env_kind) {
+    case NSGYM_ENV_FROZENLAKE:
+      return launch_table_k<NSGYM_ENV_FROZENLAKE, 3, 1>(spec, pools, io, env, n_times, prob, next, reward, done, stream);
+    case NSGYM_ENV_CLIFFWALKING:
+      return launch_table_k<NSGYM_ENV_CLIFFWALKING, 4, 1>(spec, pools, io, env, n_times, prob, next, reward, done, stream);
+    case NSGYM_ENV_BRIDGE:
+      if (!spec.split_mode)
+        return launch_table_k<NSGYM_ENV_BRIDGE, 3, 1>(spec, pools, io, env, n_times, prob, next, reward, done, stream);
+      return launch_table_k<NSGYM_ENV_BRIDGE, 3, 3>(spec, pools, io, env, n_times, prob, next, reward, done, stream);
+    default: return cudaErrorInvalidValue;
+  }
+}
+
 cudaError_t launch_grid(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& io,
                         cudaStream_t stream) {
   switch (spec.env_kind) {

@@ -54,6 +54,9 @@ cudaError_t launch_classic_f64(LaunchOp op, const NsgymSpec& spec, const DeviceP
 cudaError_t launch_grid(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& io,
                         cudaStream_t stream);
 
+cudaError_t launch_table(const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& io, int64_t env, int n_times,
+                         double* prob, int32_t* next, float* reward, uint8_t* done, cudaStream_t stream);
+
 cudaError_t launch_eval_scalar_f32(const NsgymSpec& spec, const DevicePools& pools, int slot, void* param,
                                    const int32_t* time, int32_t* istate, uint8_t* flag, void* delta,
                                    const double* inj_u, const double* inj_z, int64_t n, uint64_t seed,

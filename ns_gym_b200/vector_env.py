@@ -380,6 +380,25 @@ class NSVectorEnv:
         plan.fanout = fanout
         return plan
 
+    def transition_table(self, T: Optional[int] = None, env: int = 0):
+        """Time-indexed transition table of env ``env`` over NS times ``0..T-1`` of an episode (the
+        view of ``unwrapped.P`` / ``Bridge.transition_matrix`` step after step): ``prob [T, S, 4, D]``
+        plus the time-invariant ``next / reward / done [S, 4, D]``."""
+        if not self.program.is_grid:
+            raise ValueError("transition tables exist for the gridworld environments only")
+        spec = self.program.spec
+        T = int(T if T is not None else (spec.max_episode_steps or 100))
+        S, D = spec.nrow * spec.ncol, spec.n_dist
+        out = {"prob": torch.zeros((T, S, 4, D), dtype=torch.float64, device=self.device),
+               "next": torch.zeros((S, 4, D), dtype=torch.int32, device=self.device),
+               "reward": torch.zeros((S, 4, D), dtype=torch.float32, device=self.device),
+               "done": torch.zeros((S, 4, D), dtype=torch.uint8, device=self.device)}
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_transition_table(self._h, int(env), T, _ptr(out["prob"]), _ptr(out["next"]),
+                                                     _ptr(out["reward"]), _ptr(out["done"]), self._stream()),
+                     "nsgym_transition_table")
+        return out
+
     def snapshot(self):
         """Device copy of everything a step mutates; ``restore`` rewinds the batch to it."""
         buf = torch.empty(int(self.lib.nsgym_snapshot_bytes(self._h)), dtype=torch.uint8, device=self.device)
