@@ -49,6 +49,7 @@ WORKLOADS = {
     "c3_pendulum": dict(case="c3_pendulum", log2_envs=22, precision="fp32"),
     "c5_bridge": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64"),
     # C4: heterogeneous batch, per-env opcode rows, half CartPole (fp32) + half FrozenLake 8x8
+    # (envs bucketed by opcode signature within the shard; coefficients stay per env)
     "c4_hetero": dict(case="c4_cartpole_rows", log2_envs=23, precision="fp32", hetero=True),
     # K-step fused rollouts (state + theta in registers, device-side uniform-random policy)
     "c5_bridge_rollout8": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64", rollout_k=8),
@@ -321,7 +322,7 @@ def build_hetero(n_envs, rank, seed=0):
         rows, pool_f, pool_i, bitmap = synth_rows(kind, tmpl, half, seed * 1000 + rank * 2 + k)
         env = NSVectorEnv(case["env_id"], tp, half, precision=precision, autoreset="next_step", seed=seed,
                           env_id_offset=rank * n_envs + k * half, rows=rows,
-                          pools=(pool_f, pool_i, bitmap), **case["wrapper"], **case["make"])
+                          pools=(pool_f, pool_i, bitmap), bucket=True, **case["wrapper"], **case["make"])
         shards.append(env)
     return MixedVectorEnv(shards), CASES["c4_cartpole_rows"]
 

@@ -538,7 +538,17 @@ def compile_rows(env_id: str, params_per_env, **kwargs):
     for j in range(len(keys)):                     # a cursor plane exists if ANY env needs one
         prog.spec.slots[j].istate_plane = planes.get(j, -1)
     _attach_pools(prog, pools)
+    prog.pool_lists = (list(pools.f), list(pools.i), list(pools.bits))
     return prog, rows
+
+
+def row_signature(rows):
+    """Opcode signature of every env of a rows array: envs with equal signatures take the same
+    branches in the heterogeneous step kernel (only their coefficients differ)."""
+    sig = np.zeros(len(rows), dtype=np.int64)
+    for j in range(rows.shape[1]):
+        sig = sig * 4096 + rows["sched_op"][:, j].astype(np.int64) * 64 + rows["upd_op"][:, j].astype(np.int64)
+    return sig
 
 
 def rows_dtype():

@@ -32,7 +32,7 @@ class NSVectorEnv:
                  persistent_params: bool = False, precision: str = "fp32",
                  autoreset: str = "next_step", seed: int = 0, env_id_offset: int = 0,
                  device: Any = None, want_obs: Optional[bool] = None, want_delta: Optional[bool] = None,
-                 rows=None, pools=None, **env_kwargs):
+                 rows=None, pools=None, bucket: bool = False, **env_kwargs):
         if delta_change_notification:                         # base.py:252-255
             assert change_notification, (
                 "If change_notification is True, delta_change_notification must be True")
@@ -45,6 +45,7 @@ class NSVectorEnv:
                           scalar_reward=scalar_reward, persistent_params=persistent_params, precision=precision,
                           seed=seed, device=device, want_obs=want_obs, want_delta=want_delta, rows=rows,
                           pools=pools, env_kwargs=dict(env_kwargs))
+        self.env_order = None      # bucketed heterogeneous batches: storage position -> caller's env index
         self.lib = nv.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.num_envs = int(num_envs)
@@ -56,6 +57,8 @@ class NSVectorEnv:
             # prepared NsgymSlot array [num_envs, n_slots] -- the key-set template of the batch
             if rows is True:
                 self.program, self.rows = compile_rows(env_id, tunable_params, **compile_kw)
+                pools = self.program.pool_lists
+                self._ctor["tunable_params"] = tunable_params[0]      # key-set template for planning copies
             else:
                 self.program = compile_program(env_id, tunable_params, num_envs, **compile_kw)
                 self.rows = np.ascontiguousarray(rows)
@@ -70,6 +73,14 @@ class NSVectorEnv:
                         self.rows["istate_plane"][sel, j] = planes
             if len(self.rows) != self.num_envs:
                 raise ValueError(f"{len(self.rows)} rows for {self.num_envs} envs")
+            self._ctor["pools"] = pools
+            if bucket:
+                # bucket the envs by opcode signature: warps of the heterogeneous kernel then
+                # hold envs that take the same branches.  Storage position k holds the caller's env
+                # env_order[k]; actions / results are in storage order.
+                from .compile import row_signature
+                self.env_order = np.argsort(row_signature(self.rows), kind="stable")
+                self.rows = np.ascontiguousarray(self.rows[self.env_order])
             if pools is not None:
                 # prepared rows index their own pools (pool_f doubles, pool_i int32, bitmap uint32)
                 from .compile import _Pools, _attach_pools
@@ -142,10 +153,24 @@ class NSVectorEnv:
         self._zeros_u8 = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._zeros_real = torch.zeros(n, dtype=self.real, device=self.device)
 
+    def to_storage(self, x):
+        """Reorder a per-env array / tensor from the caller's env order to storage order."""
+        return x if self.env_order is None else x[torch.as_tensor(self.env_order, device=x.device)
+                                                  if torch.is_tensor(x) else self.env_order]
+
+    def to_caller(self, x):
+        """Reorder a per-env array / tensor (leading env axis) from storage order back to the caller's."""
+        if self.env_order is None:
+            return x
+        inv = np.empty_like(self.env_order)
+        inv[self.env_order] = np.arange(len(self.env_order))
+        return x[torch.as_tensor(inv, device=x.device) if torch.is_tensor(x) else inv]
+
     @classmethod
     def heterogeneous(cls, env_id: str, params_per_env, **kwargs):
         """BASELINE config C4: one ``tunable_params`` dict PER ENV (same parameter names, per-env
-        schedulers / update functions / coefficients)."""
+        schedulers / update functions / coefficients).  ``bucket=True`` stores the envs sorted by
+        opcode signature (``env_order``; see ``to_storage`` / ``to_caller``)."""
         params_per_env = list(params_per_env)
         return cls(env_id, params_per_env, len(params_per_env), rows=True, **kwargs)
 
@@ -355,11 +380,8 @@ class NSVectorEnv:
         if limit is not None:
             kw["max_episode_steps"] = limit
         rows, tp = c["rows"], c["tunable_params"]
-        if rows is not None:
-            if rows is True:                          # one dict per env -> repeat the dicts
-                tp = [d for d in tp for _ in range(fanout)]
-            else:
-                rows = np.repeat(self.rows, fanout, axis=0)
+        if rows is not None:                          # per-env rows (already in storage order): repeat them
+            rows = np.repeat(self.rows, fanout, axis=0)
         if seed is None:
             seed = (int(self.program.spec.seed) * 0x9E3779B97F4A7C15 + int(self.lib.nsgym_step_index(self._h)) + 1) \
                 & (2**64 - 1)
