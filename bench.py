@@ -70,7 +70,7 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index: int, period_ms: int = 50):
+    def __init__(self, index: int, period_ms: int = 20):
         self.samples = []
         self.proc = None
         self.index = index
@@ -428,7 +428,6 @@ def run_gpu(args):
     rollout_k = int(wl.get("rollout_k", 0))
     per_launch = max(rollout_k, 1)                     # env-steps each env advances per launch
     secs = time_steps(shards, actions, args.steps, max(args.warmup, 3), dist, rollout_k)
-    sampler.mark(1)
     launches = env.launch_count - launches0 - max(args.warmup, 3) * len(shards)
     t = torch.tensor([secs], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -488,6 +487,7 @@ def run_gpu(args):
         e2e_step()
     torch.cuda.synchronize()
     e2e_secs = time.perf_counter() - t0
+    sampler.mark(1)            # clocks are sampled over both timed regions (device-resident and end-to-end)
     t = torch.tensor([e2e_secs], dtype=torch.float64, device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
