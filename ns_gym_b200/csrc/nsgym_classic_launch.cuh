@@ -21,8 +21,14 @@ template <> struct TrueMin<double> { static constexpr double value = 4.940656458
 
 // Lower one ABI slot to the kernel's form (SlotT): fast / slow class, range gate in unsigned
 // form, multiply-high modulo, affine coefficients, constraint threshold.
+// t_max: largest NS time the handle can reach (TimeLimit + autoreset), or 2^28
+inline int64_t reachable_t_max(const NsgymSpec& spec) {
+  return (spec.autoreset == NSGYM_AUTORESET_NEXT_STEP && spec.max_episode_steps > 0)
+             ? int64_t(spec.max_episode_steps) + 1 : (int64_t(1) << 28);
+}
+
 template <typename R>
-static SlotT<R> lower_slot(const NsgymSlot& a, int lane) {
+static SlotT<R> lower_slot(const NsgymSlot& a, int lane, int64_t t_max = (int64_t(1) << 28)) {
   SlotT<R> b{};
   b.lane = lane;
   b.sched_op = a.sched_op; b.upd_op = a.upd_op; b.constraint = a.constraint;
@@ -59,6 +65,12 @@ static SlotT<R> lower_slot(const NsgymSlot& a, int lane) {
     case NSGYM_UPD_ADD_T: Ct = a.uf[0]; break;
     case NSGYM_UPD_MUL: A = a.uf[0]; break;
     case NSGYM_UPD_RW: B = a.uf[0]; Ct = a.uf[3]; b.flags |= SF_NORMAL; break;
+    case NSGYM_UPD_LERP: case NSGYM_UPD_MUL_EXP: case NSGYM_UPD_SIGMOID:
+      b.flags |= std::is_same<R, float>::value ? SF_MEDIUM : SF_SLOW_UPD;
+      break;
+    case NSGYM_UPD_ADD_SIN:    // the bounded sine is good for t <= 1e5
+      b.flags |= (std::is_same<R, float>::value && t_max <= 100000) ? SF_MEDIUM : SF_SLOW_UPD;
+      break;
     default: b.flags |= SF_SLOW_UPD; break;
   }
   b.fa[0] = R(A); b.fa[1] = R(B); b.fa[2] = R(Ct);
@@ -92,7 +104,7 @@ static ProgramT<R, NP> build_program(const NsgymSpec& spec, const DevicePools& p
   for (int j = 0; j < NP; ++j) {
     const NsgymSlot& a = spec.slots[j];
     SlotT<R>& b = P.slot[j];
-    b = lower_slot<R>(a, j);
+    b = lower_slot<R>(a, j, reachable_t_max(spec));
     b.theta_index = a.theta_index;
     b.init = R(spec.theta_init[a.theta_index][0]);
     b.partner_slot = a.partner_slot;
@@ -139,7 +151,7 @@ static void row_words(const SlotT<R>& b, const NsgymSlot& a, int32_t (&iw)[kRowI
   iw[RI_MOD] = mod; iw[RI_MAGIC] = (flags & SF_SLOW_SCHED) ? 0 : b.mod_magic;
   iw[RI_SI0] = a.si[0]; iw[RI_SI1] = a.si[1]; iw[RI_UI0] = a.ui[0]; iw[RI_UI1] = a.ui[1];
   iw[RI_IINIT] = a.istate_init;
-  if (flags & SF_SLOW_UPD) {
+  if (flags & (SF_SLOW_UPD | SF_MEDIUM)) {
     for (int k = 0; k < kRowReal; ++k) rw[k] = double(b.uf[k]);
   } else {
     rw[0] = double(b.fa[0]); rw[1] = double(b.fa[1]); rw[2] = double(b.fa[2]);
@@ -217,19 +229,31 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       return cudaGetLastError();
     }
   }
-  // programs without slow-class slots run the lean instantiation (no rule switches compiled in)
-  const bool slow = P.n_slow > 0;
+  // programs without slow-class slots run a lean instantiation (no rule switches compiled in):
+  // level 0 = fast class only, level 1 = + inline medium rules (fp32 fast mode), level 2 = everything
+  int level = P.n_slow > 0 ? 2 : 0;
+  if (level == 0)
+    for (int j = 0; j < NP; ++j)
+      if (P.slot[j].flags & SF_MEDIUM) level = 1;
+  constexpr bool kHasMedium = std::is_same<R, float>::value;
   switch (op) {
     case OP_STEP:
-      if (slow) classic_step_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, io);
-      else classic_step_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, io);
+      if (level == 2) classic_step_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io);
+      else if (level == 1) {
+        if constexpr (kHasMedium) classic_step_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, io);
+        else return cudaErrorInvalidValue;
+      } else classic_step_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, io);
       break;
-    case OP_RESET: classic_reset_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, io); break;
+    case OP_RESET: classic_reset_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io); break;
     case OP_ROLLOUT:
-      if (slow || NP == 0)
-        classic_rollout_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
-      else
-        classic_rollout_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+      if (level == 2 || NP == 0)
+        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+      else if (level == 1) {
+        if constexpr (kHasMedium)
+          classic_rollout_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+        else return cudaErrorInvalidValue;
+      } else
+        classic_rollout_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
       break;
   }
   return cudaGetLastError();

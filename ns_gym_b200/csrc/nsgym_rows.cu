@@ -19,7 +19,7 @@ void lower_row(const NsgymSpec& spec, const NsgymSlot& src, int j, int32_t (&iw)
                double (&dw)[kRowDbl]) {
   NsgymSlot a = src;
   set_mod_magic(&a, spec);
-  const SlotT<R> b = lower_slot<R>(a, j);
+  const SlotT<R> b = lower_slot<R>(a, j, reachable_t_max(spec));
   row_words<R>(b, a, iw, rw, dw);
 }
 
