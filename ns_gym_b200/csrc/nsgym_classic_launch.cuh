@@ -222,7 +222,10 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     else {
       const HetT<R, NP> H = build_het<R, NP>(*a.rows);
       switch (op) {
-        case OP_STEP: classic_step_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
+        case OP_STEP:
+          if (a.rows->lean) classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
+          else classic_step_het_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, H, io);
+          break;
         case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
         default: return cudaErrorNotSupported;
       }

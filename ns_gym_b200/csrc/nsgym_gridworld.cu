@@ -53,7 +53,10 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   if (a.rows && a.rows->active) {
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     switch (op) {
-      case OP_STEP: grid_step_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
+      case OP_STEP:
+        if (a.rows->lean) grid_step_het_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, H, io);
+        else grid_step_het_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, H, io);
+        break;
       case OP_RESET: grid_reset_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
       default: return cudaErrorNotSupported;
     }

@@ -31,6 +31,7 @@ struct RowTable {
   double def_real[NSGYM_MAX_SLOTS][kRowReal] = {};
   double def_dbl[NSGYM_MAX_SLOTS][kRowDbl] = {};
   double bytes_per_env = 0.0;
+  bool lean = false;     // no row uses a stochastic scheduler, a cursor / slow update rule or a Dirichlet draw
 };
 
 // untyped view of StepIO<R>; the typed launchers reinterpret the real-valued pointers

@@ -29,6 +29,7 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
   const int np = spec.n_slots;
   RowTable t;
   t.active = true;
+  t.lean = true;
   t.precision = std::is_same<R, double>::value ? NSGYM_F64 : NSGYM_F32;
   int32_t iw[kRowInt];
   double rw[kRowReal], dw[kRowDbl];
@@ -54,6 +55,14 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
       }
       if (int rc = validate_row_slot(&spec, &a, j, err, err_len)) return rc;
       lower_row<R>(spec, a, j, iw, rw, dw);
+      {   // lean kernels: deterministic schedulers; fast / medium scalar rules or deterministic distribution rules
+        const bool det_sched = a.sched_op != NSGYM_SCHED_RANDOM && a.sched_op != NSGYM_SCHED_DECAY &&
+                               a.sched_op != NSGYM_SCHED_MEMORYLESS;
+        const bool dist = a.upd_op >= NSGYM_UPD_D_NOP;
+        const bool lean_upd = dist ? (a.upd_op != NSGYM_UPD_D_RANDOM && a.ui[2] == 0)
+                                   : !((iw[RI_OPS] & 0xFF) & SF_SLOW_UPD);
+        t.lean = t.lean && det_sched && lean_upd;
+      }
       uint32_t m = 0;
       for (int w = 0; w < kRowInt; ++w) m |= (iw[w] != t.def_int[j][w]) ? (1u << w) : 0u;
       for (int w = 0; w < kRowReal; ++w)

@@ -62,6 +62,26 @@ def _c4_scalar(S, U, r, y0, scale):
     return U.RandomWalk(sch, mu=float(r.uniform(-0.02, 0.02)) * scale, sigma=float(r.uniform(0.0, 0.3)) * scale)
 
 
+def _het_cartpole_lean(S, U, e):
+    """rows of the fast class only (any precision): the lean heterogeneous kernel"""
+    r = np.random.default_rng([7, e])
+
+    def one(scale):
+        sch = _c4_scheduler(S, r)
+        k = int(r.integers(0, 5))
+        if k == 0:
+            return U.IncrementUpdate(sch, k=float(r.uniform(0.1, 1.0)) * scale)
+        if k == 1:
+            return U.DecrementUpdate(sch, k=float(r.uniform(0.01, 0.2)) * scale)
+        if k == 2:
+            return U.DeterministicTrend(sch, slope=float(r.uniform(-0.01, 0.02)) * scale)
+        if k == 3:
+            return U.GeometricProgression(sch, r=float(r.uniform(0.98, 1.03)))
+        return U.RandomWalkWithDrift(sch, alpha=0.01 * scale, mu=0.0, sigma=float(r.uniform(0.0, 0.3)) * scale)
+
+    return {"force_mag": one(1.0), "length": one(0.02), "gravity": one(0.5)}
+
+
 def _c4_cartpole(S, U, e):
     r = np.random.default_rng([4, e])
     return {"masspole": _c4_scalar(S, U, r, 0.1, 0.01), "gravity": _c4_scalar(S, U, r, 9.8, 0.5)}
@@ -364,6 +384,9 @@ CASES = {
         "FrozenLake-v1", _c4_frozenlake,
         wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True, delta_change_notification=True),
         make=dict(MAP8, max_episode_steps=200), steps=150),
+    "het_cartpole_lean": _het(
+        "CartPole-v1", _het_cartpole_lean,
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),
     "het_cartpole_wide": _het(
         "CartPole-v1", _het_cartpole_wide,
         wrapper=dict(change_notification=True, delta_change_notification=True), steps=80),

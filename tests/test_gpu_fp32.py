@@ -21,7 +21,8 @@ pytestmark = pytest.mark.gpu
 
 FP32_CASES = ["c1_cartpole_readme", "cartpole_all_params", "cartpole_lists", "cartpole_stochastic",
               "cartpole_constraint", "cartpole_persistent", "c3_acrobot", "c3_mountaincar", "c3_pendulum",
-              "mountaincar_continuous", "pendulum_all"]
+              "mountaincar_continuous", "pendulum_all",
+              "c4_cartpole_rows", "het_cartpole_lean"]      # heterogeneous rows: the lean per-env kernel
 
 
 @pytest.mark.parametrize("name", FP32_CASES)
