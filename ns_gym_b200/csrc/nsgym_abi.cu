@@ -411,7 +411,6 @@ int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d
   if (!h || !h->bound) return fail(-1, "handle not bound");
   if (!h->initialised) return fail(-4, "rollout before reset");
   if (policy != 0) return fail(-1, "only policy 0 (uniform random) is implemented");
-  if (h->rows.active) return fail(-5, "fused rollouts of heterogeneous handles are not implemented");
   if (k_steps <= 0) return fail(-1, "k_steps must be positive");
   nsg::LaunchIO io = base_io(h);
   io.k_steps = k_steps;

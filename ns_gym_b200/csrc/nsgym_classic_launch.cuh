@@ -227,11 +227,15 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
           else classic_step_het_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, H, io);
           break;
         case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
-        default: return cudaErrorNotSupported;
+        case OP_ROLLOUT:
+          classic_rollout_kernel<R, KIND, NP, 2, true><<<grid, block, 0, stream>>>(P, H, io, a.k_steps, a.gamma, a.ret,
+                                                                                  a.len);
+          break;
       }
       return cudaGetLastError();
     }
   }
+  const HetT<R, NP> no_rows{};
   // programs without slow-class slots run a lean instantiation (no rule switches compiled in):
   // level 0 = fast class only, level 1 = + inline medium rules (fp32 fast mode), level 2 = everything
   int level = P.n_slow > 0 ? 2 : 0;
@@ -250,13 +254,13 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     case OP_RESET: classic_reset_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io); break;
     case OP_ROLLOUT:
       if (level == 2 || NP == 0)
-        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
       else if (level == 1) {
         if constexpr (kHasMedium)
-          classic_rollout_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+          classic_rollout_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
         else return cudaErrorInvalidValue;
       } else
-        classic_rollout_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, io, a.k_steps, a.gamma, a.ret, a.len);
+        classic_rollout_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
       break;
   }
   return cudaGetLastError();

@@ -58,11 +58,15 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
         else grid_step_het_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, H, io);
         break;
       case OP_RESET: grid_reset_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
-      default: return cudaErrorNotSupported;
+      case OP_ROLLOUT:
+        grid_rollout_kernel<KIND, D, MAXP, true, true><<<grid, block, 0, stream>>>(G, H, io, a.k_steps, a.gamma, a.ret,
+                                                                                  a.len);
+        break;
     }
     return cudaGetLastError();
   }
   // lean instantiation when every bound rule is deterministic
+  const HetT<double, MAXP> no_rows{};
   bool slow = false;
   for (int j = 0; j < spec.n_slots; ++j) {
     const NsgymSlot& sl = spec.slots[j];
@@ -76,8 +80,8 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
       break;
     case OP_RESET: grid_reset_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
     case OP_ROLLOUT:
-      if (slow) grid_rollout_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, io, a.k_steps, a.gamma, a.ret, a.len);
-      else grid_rollout_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, io, a.k_steps, a.gamma, a.ret, a.len);
+      if (slow) grid_rollout_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
+      else grid_rollout_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
       break;
   }
   return cudaGetLastError();

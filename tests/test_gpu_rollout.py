@@ -105,3 +105,60 @@ def test_device_philox_matches_numpy_restatement():
                      ((w >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)) for w in words], 1)
     got = env.buffers["state"].cpu().numpy()
     np.testing.assert_allclose(got, want, rtol=0, atol=1e-8)
+
+
+@pytest.mark.parametrize("name,kind", [("c4_cartpole_rows", "cartpole"), ("het_cartpole_wide", "cartpole"),
+                                       ("c4_frozenlake8_rows", "grid"), ("het_bridge_split", "grid")])
+def test_heterogeneous_rollout_equals_single_steps(name, kind):
+    """Per-env rows: the fused rollout and K single-step launches run the same device arithmetic."""
+    import torch
+
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.vector_env import NSVectorEnv
+
+    case, n, K, seed = CASES[name], 512, 29, 77
+    per_env = [case["params_of"](PS, PU, e) for e in range(n)]
+    kw = dict(precision="fp64", seed=seed, **case["wrapper"], **case["make"])
+    a = NSVectorEnv.heterogeneous(case["env_id"], per_env, **kw)
+    b = NSVectorEnv.heterogeneous(case["env_id"], per_env, **kw)
+    a.reset(seed=seed)
+    b.reset(seed=seed)
+    step0 = int(a.lib.nsgym_step_index(a._h))
+    ret, length = a.rollout(K, gamma=1.0)
+    gids = np.arange(n, dtype=np.uint64)
+    acc = torch.zeros(n, dtype=torch.float32, device=b.device)
+    for k in range(K):
+        act = philox_np.policy_actions(kind, gids, step0 + k, seed)
+        obs, r, term, trunc, info = b.step(torch.as_tensor(act))
+        acc += r
+    torch.cuda.synchronize()
+    for key in ("state", "theta", "t", "istate"):
+        x, y = a.buffers[key], b.buffers[key]
+        if x is not None:
+            assert torch.equal(x, y), f"{name}: {key} differs after the rollout"
+    assert torch.equal(ret, acc)
+
+
+def test_planning_fanout_on_a_heterogeneous_batch():
+    import torch
+
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.vector_env import NSVectorEnv
+
+    case, n, m = CASES["c4_cartpole_rows"], 128, 4
+    env = NSVectorEnv.heterogeneous(case["env_id"], [case["params_of"](PS, PU, e) for e in range(n)], bucket=True,
+                                    precision="fp32", seed=3, change_notification=True,
+                                    delta_change_notification=True, in_sim_change=True)
+    env.reset(seed=3)
+    a = torch.zeros(n, dtype=torch.int32, device=env.device)
+    for _ in range(5):
+        env.step(a)
+    plan = env.get_planning_env(fanout=m)
+    assert torch.equal(plan.buffers["theta"], env.buffers["theta"].repeat_interleave(m, dim=1))
+    assert np.array_equal(plan.rows, np.repeat(env.rows, m, axis=0))
+    ret, length = plan.rollout(40, gamma=0.95)
+    assert bool(torch.isfinite(ret).all()) and int(length.min()) >= 1
+    # the copies keep evolving (in_sim_change): some parameter moved away from its root's value
+    assert not torch.equal(plan.buffers["theta"], env.buffers["theta"].repeat_interleave(m, dim=1))
