@@ -98,3 +98,53 @@ def test_scheduler_known_answers(ka):
     got = [bool(call(1.0, t)[1]) for t in times]
     assert got == want
     call.destroy()
+
+
+def test_bridge_transitions_known_answers():
+    """The reference's own Bridge tests (tests/test_bridge.py:135-224): action -> cell map, out of
+    bounds, forced slip, the side-local distribution in split mode, reward / done from the
+    destination cell -- one env per case, cells planted in the state buffer."""
+    import torch
+
+    import ns_gym_b200 as nsb
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200.wrappers import NSBridgeWrapper
+
+    ncol = 8
+
+    def st(r, c):
+        return r * ncol + c
+
+    def run(tunable, init, cases):
+        env = NSBridgeWrapper(nsb.make("ns_gym/Bridge-v0", num_envs=len(cases)), tunable, initial_prob_dist=init,
+                              autoreset="none")
+        env.reset(seed=0)
+        env.buffers["state"].copy_(torch.tensor([c[0] for c in cases], dtype=torch.int32))
+        obs, r, term, trunc, info = env.step(torch.tensor([c[1] for c in cases], dtype=torch.int32))
+        return obs["state"].cpu().tolist(), r.cpu().tolist(), term.cpu().tolist()
+
+    nop = lambda: PU.DistributionNoUpdate(PS.ContinuousScheduler())            # noqa: E731
+    # test_bridge.py:135-175 deterministic P = [1, 0, 0]
+    cases = [(st(2, 4), 0, st(2, 3)), (st(2, 4), 1, st(3, 4)), (st(2, 4), 2, st(2, 5)), (st(2, 4), 3, st(1, 4)),
+             (st(1, 1), 0, st(1, 0)), (st(1, 1), 1, st(2, 1)), (st(1, 1), 2, st(1, 2)),
+             (st(1, 0), 0, st(1, 0)), (st(2, 7), 2, st(2, 7)), (st(0, 0), 3, st(0, 0)), (st(0, 0), 0, st(0, 0))]
+    got, _, _ = run({"P": nop()}, [1.0, 0.0, 0.0], cases)
+    assert got == [c[2] for c in cases]
+    # :178-197 forced slip to (a + 1) % 4 from S = (2, 4)
+    cases = [(st(2, 4), a, st(*rc)) for a, rc in {0: (3, 4), 1: (2, 5), 2: (1, 4), 3: (2, 3)}.items()]
+    got, _, _ = run({"P": nop()}, [0.0, 1.0, 0.0], cases)
+    assert got == [c[2] for c in cases]
+    # :200-224 split mode: the side of the CURRENT cell selects the distribution (col < ncol // 2 = left)
+    cases = [(st(2, 1), 0, st(2, 0)),          # left side, P_left = [1, 0, 0]: LEFT goes left
+             (st(2, 6), 0, st(3, 6)),          # right side, P_right = [0, 1, 0]: LEFT slips to DOWN
+             (st(2, 3), 2, st(2, 4)),          # col 3 is still the left side
+             (st(2, 4), 2, st(1, 4))]          # col 4 is the right side: RIGHT slips to UP
+    got, _, _ = run({"P_left": nop(), "P_right": nop()}, ([1.0, 0.0, 0.0], [0.0, 1.0, 0.0]), cases)
+    assert got == [c[2] for c in cases]
+    # envs/Bridge.py:159-174 reward / done from the destination; no absorbing cells (S16)
+    cases = [(st(2, 4), 3, st(1, 4)), (st(1, 4), 3, st(0, 4)), (st(0, 4), 1, st(1, 4)), (st(2, 6), 2, st(2, 7)),
+             (st(2, 1), 0, st(2, 0))]
+    got, rew, term = run({"P": nop()}, [1.0, 0.0, 0.0], cases)
+    assert got == [c[2] for c in cases]
+    assert rew == [0.0, -1.0, 0.0, 1.0, 1.0] and term == [False, True, False, True, True]
