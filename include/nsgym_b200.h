@@ -293,6 +293,13 @@ int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_
                       const double* d_inj_uniform, const double* d_inj_normal, int64_t n,
                       void* stream);
 
+/* Handle options.  NSGYM_OPT_GENERAL_KERNELS != 0: always launch the general kernel instantiations
+ * (all rule classes, injection-capable) instead of the lean ones the library would pick for this
+ * program -- same results (bit for bit in fp64 mode), used by the tests to tie the lean kernels to
+ * the oracle-checked general ones. */
+enum { NSGYM_OPT_GENERAL_KERNELS = 1 };
+int nsgym_set_option(NsgymHandle* h, int option, int64_t value);
+
 /* replaces: reset(seed=...) reseeding (base.py:386-388, 412-421): re-keys the Philox streams */
 void nsgym_set_seed(NsgymHandle* h, uint64_t seed);
 uint64_t nsgym_step_index(const NsgymHandle* h);        /* Philox counter (launches so far) */

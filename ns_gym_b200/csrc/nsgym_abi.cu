@@ -51,6 +51,7 @@ struct NsgymHandle {
   bool streams_ready = false;
   nsg::RowTable rows;              // heterogeneous handles (nsgym_create_rows)
   int32_t plan_elapsed = -1;       // planning copy (nsgym_fanout): TimeLimit steps since the copy
+  int32_t general_kernels = 0;     // NSGYM_OPT_GENERAL_KERNELS
 
   bool grid() const { return nsg::is_grid_kind(spec.env_kind); }
   size_t real_bytes() const { return grid() ? 8 : (spec.precision == NSGYM_F64 ? 8 : 4); }
@@ -74,6 +75,7 @@ nsg::LaunchIO base_io(const NsgymHandle* h) {
   io.gamma = 1.f;
   io.rows = h->rows.active ? &h->rows : nullptr;
   io.plan_elapsed = h->plan_elapsed;
+  io.general_kernels = h->general_kernels;
   return io;
 }
 
@@ -571,6 +573,14 @@ int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_
   if (e != cudaSuccess) return fail(-10, "eval launch: %s", cudaGetErrorString(e));
   h->step_index += 1;
   return 0;
+}
+
+int nsgym_set_option(NsgymHandle* h, int option, int64_t value) {
+  if (!h) return fail(-1, "NULL handle");
+  switch (option) {
+    case NSGYM_OPT_GENERAL_KERNELS: h->general_kernels = value != 0; return 0;
+    default: return fail(-1, "unknown option %d", option);
+  }
 }
 
 void nsgym_set_seed(NsgymHandle* h, uint64_t seed) { if (h) h->spec.seed = seed; }

@@ -223,7 +223,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       const HetT<R, NP> H = build_het<R, NP>(*a.rows);
       switch (op) {
         case OP_STEP:
-          if (a.rows->lean) classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
+          if (a.rows->lean && !a.general_kernels) classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
           else classic_step_het_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, H, io);
           break;
         case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
@@ -238,7 +238,9 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   const HetT<R, NP> no_rows{};
   // programs without slow-class slots run a lean instantiation (no rule switches compiled in):
   // level 0 = fast class only, level 1 = + inline medium rules (fp32 fast mode), level 2 = everything
-  int level = P.n_slow > 0 ? 2 : 0;
+  // (injected random tables -- parity tests -- also take level 2: the lean kernels fold the
+  // "injected?" tests away)
+  int level = (P.n_slow > 0 || a.inj_u || a.inj_z || a.general_kernels) ? 2 : 0;
   if (level == 0)
     for (int j = 0; j < NP; ++j)
       if (P.slot[j].flags & SF_MEDIUM) level = 1;

@@ -42,6 +42,7 @@ struct LaunchIO {
   int64_t n, begin, count;
   uint64_t gid_offset, seed, step_index;
   int32_t skip_updates, force_init, prefetch, plan_elapsed;
+  int32_t general_kernels;   // NSGYM_OPT_GENERAL_KERNELS
   // rollout
   int32_t k_steps; float gamma; float* ret; int32_t* len;
   const RowTable* rows;   // heterogeneous handles

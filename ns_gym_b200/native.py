@@ -32,6 +32,8 @@ UPD_D_TARGET, UPD_D_LERP, UPD_D_STEPWISE, UPD_D_CYCLIC, UPD_D_RANDOM = 36, 37, 3
 
 CONS_NONE, CONS_REJECT_LE0, CONS_REJECT_LT0, CONS_ACRO_LENGTH1, CONS_ACRO_COM = 0, 1, 2, 3, 4
 
+OPT_GENERAL_KERNELS = 1
+
 T_ENDED = 0x80000000
 T_TERMINATED_ONCE = 0x40000000
 T_TABLE_FRESH = 0x20000000
@@ -90,7 +92,7 @@ class NsgymHostOut(C.Structure):
 EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
     "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_step_host",
-    "nsgym_rollout", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_eval_update", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
+    "nsgym_rollout", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
     "nsgym_launch_count",
 ]
 
@@ -145,6 +147,7 @@ def load(build_if_missing: bool = False):
     lib.nsgym_restore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
     lib.nsgym_transition_table.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
+    lib.nsgym_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
     lib.nsgym_eval_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]

@@ -421,6 +421,12 @@ class NSVectorEnv:
                      "nsgym_transition_table")
         return out
 
+    def set_option(self, name: str, value) -> None:
+        """Handle options (``nsgym_set_option``): ``"general_kernels"`` forces the general kernel
+        instantiations instead of the lean ones picked for this program (same results)."""
+        opt = {"general_kernels": nv.OPT_GENERAL_KERNELS}[name]
+        nv.check(self.lib.nsgym_set_option(self._h, opt, int(value)), "nsgym_set_option")
+
     def snapshot(self):
         """Device copy of everything a step mutates; ``restore`` rewinds the batch to it."""
         buf = torch.empty(int(self.lib.nsgym_snapshot_bytes(self._h)), dtype=torch.uint8, device=self.device)
