@@ -223,7 +223,8 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       const HetT<R, NP> H = build_het<R, NP>(*a.rows);
       switch (op) {
         case OP_STEP:
-          if (a.rows->lean && !a.general_kernels) classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
+          if (a.rows->lean && !a.general_kernels && !a.inj_u && !a.inj_z)
+            classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
           else classic_step_het_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, H, io);
           break;
         case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;

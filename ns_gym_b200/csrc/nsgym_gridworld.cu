@@ -54,7 +54,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     switch (op) {
       case OP_STEP:
-        if (a.rows->lean && !a.general_kernels) grid_step_het_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, H, io);
+        if (a.rows->lean && !a.general_kernels && !a.inj_u) grid_step_het_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, H, io);
         else grid_step_het_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, H, io);
         break;
       case OP_RESET: grid_reset_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
@@ -67,7 +67,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   }
   // lean instantiation when every bound rule is deterministic
   const HetT<double, MAXP> no_rows{};
-  bool slow = a.general_kernels != 0;
+  bool slow = a.general_kernels != 0 || a.inj_u != nullptr;     // the lean kernels fold the injection tests away
   for (int j = 0; j < spec.n_slots; ++j) {
     const NsgymSlot& sl = spec.slots[j];
     slow |= sl.sched_op == NSGYM_SCHED_RANDOM || sl.sched_op == NSGYM_SCHED_DECAY ||
