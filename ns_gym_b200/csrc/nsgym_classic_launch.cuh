@@ -246,13 +246,14 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     for (int j = 0; j < NP; ++j)
       if (P.slot[j].flags & SF_MEDIUM) level = 1;
   constexpr bool kHasMedium = std::is_same<R, float>::value;
+  const unsigned lean_grid = unsigned((a.count + block * NSGYM_LEAN_EPT - 1) / (block * NSGYM_LEAN_EPT));
   switch (op) {
     case OP_STEP:
       if (level == 2) classic_step_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io);
       else if (level == 1) {
-        if constexpr (kHasMedium) classic_step_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, io);
+        if constexpr (kHasMedium) classic_step_kernel<R, KIND, NP, 1><<<lean_grid, block, 0, stream>>>(P, io);
         else return cudaErrorInvalidValue;
-      } else classic_step_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, io);
+      } else classic_step_kernel<R, KIND, NP, 0><<<lean_grid, block, 0, stream>>>(P, io);
       break;
     case OP_RESET: classic_reset_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io); break;
     case OP_ROLLOUT:
