@@ -162,14 +162,15 @@ def _cpu_actions(case_name):
     return functools.partial(draw_cpu_actions, case_name)
 
 
-def cpu_baseline(case_name, n_envs_per_proc=64, n_steps=600, n_procs=None):
+def cpu_baseline(case_name, n_envs_per_proc=64, n_steps=8000, n_procs=None):
     """env-steps/s of the oracle port with one Sync vector loop per host core."""
     from oracle import vector
 
     make, case = _cpu_make_envs(case_name)
     draw = _cpu_actions(case_name)
     cores = n_procs or os.cpu_count() or 1
-    sync = vector.run_sync(make, n_envs_per_proc, max(n_steps // 4, 50), draw)
+    # bounded sample: ~10 s of CPU work per core (the port runs ~8e4 env-steps/s per core)
+    sync = vector.run_sync(make, n_envs_per_proc, max(n_steps // 8, 50), draw)
     par = vector.run_parallel(make, n_envs_per_proc, n_steps, draw, cores) if cores > 1 else sync
     return {
         "value": par, "unit": UNIT, "cores": cores, "kind": "port",
@@ -197,7 +198,7 @@ def run_reference(args):
     steps = max(args.steps, 1)
     # each bench "step" here = one vector step of `per_step` envs per process; bounded so the
     # whole run ends within a few minutes
-    n_steps = min(steps * 10, 1500)
+    n_steps = min(max(steps, 1) * 25, 10000)         # 400 steps -> 10000 vector steps ~ 10 s per core
     warm = vector.run_sync(make, per_step, max(args.warmup, 3), draw)
     del warm
     t0 = time.perf_counter()

@@ -82,6 +82,14 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
       if ((t.mask[j] >> (kRowInt + kRowReal + w)) & 1u) t.plane[j][kRowInt + kRowReal + w] = uint8_t(t.n_dbl++);
   }
   t.bytes_per_env = 4.0 * t.n_int + double(sizeof(R)) * t.n_real + 8.0 * t.n_dbl;
+  {   // the kernels index planes with 32-bit arithmetic
+    const int widest = t.n_int > t.n_real ? (t.n_int > t.n_dbl ? t.n_int : t.n_dbl) : (t.n_real > t.n_dbl ? t.n_real : t.n_dbl);
+    if (uint64_t(widest) * uint64_t(n) >= (1ull << 32)) {
+      snprintf(err, err_len, "%d row planes x %lld envs exceed 32-bit plane indexing: split the batch into shards",
+               widest, (long long)n);
+      return -1;
+    }
+  }
   // ---- pass 2: fill the planes ----
   std::vector<int32_t> hi(size_t(t.n_int) * n);
   std::vector<R> hr(size_t(t.n_real) * n);
