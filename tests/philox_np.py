@@ -31,13 +31,13 @@ BLK_POLICY = 13
 
 def policy_actions(kind, gids, step_index, seed):
     """The rollout kernels' uniform-random policy (nsgym_device.cuh / nsgym_grid.cuh)."""
+    if kind == "grid":      # word z of block 0 (words x, y feed the slip draw)
+        return (block(gids, step_index, 0, seed)[2] >> np.uint32(30)).astype(np.int32)
     x = block(gids, step_index, BLK_POLICY, seed)[0]
     if kind == "cartpole":
         return (x >> np.uint32(31)).astype(np.int32)
     if kind in ("acrobot", "mountaincar"):
         return ((x.astype(np.uint64) * np.uint64(3)) >> np.uint64(32)).astype(np.int32)
-    if kind == "grid":
-        return (x >> np.uint32(30)).astype(np.int32)
     u = (x >> np.uint32(8)).astype(np.float32) * np.float32(1.0 / 16777216.0)
     if kind == "pendulum":
         return np.float32(-2) + np.float32(4) * u
