@@ -202,6 +202,23 @@ class NSVectorEnv:
     def action_space_n(self):
         return N_ACTIONS.get(self.program.env_kind)
 
+    @property
+    def action_space(self):
+        """``Discrete(n)`` or ``Box(low, high)`` of the base env; ``sample()`` draws one action per env."""
+        from .spaces import Box, Discrete
+        kind = self.program.env_kind
+        if kind in BOX_ACTION:
+            lo, hi = BOX_ACTION[kind]
+            return Box(lo, hi, (1,), self.num_envs, self.device, self.real)
+        return Discrete(N_ACTIONS[kind], self.num_envs, self.device)
+
+    single_action_space = action_space
+
+    @property
+    def t(self):
+        """``NSWrapper.t`` per env (``base.py:314``)."""
+        return self.relative_time()
+
     # ------------------------------------------------------------------------------------
     def reset(self, *, seed: Optional[int] = None, options=None, mask: Optional[torch.Tensor] = None,
               inject_uniform: Optional[torch.Tensor] = None):

@@ -122,18 +122,20 @@ def table_of(env):
     return out
 
 
-def oracle_table_trace(builder, case, T, seed=3):
-    """Tables in force at NS times 0..T-1 of ONE env stepped from a reset (stepping past episode
-    ends: the parameters keep evolving with t): prob [T, S, A, D] + the time-invariant part."""
-    actions = harness.draw_actions(case, seed + 1, T, 1)
-    clock, per_env, _, _ = harness.make_streams(seed, 1, T + 1, n_slots_of(case))
-    envs = builder(case, 1, per_env)
+def oracle_table_trace(builder, case, T, seed=3, env=0):
+    """Tables in force at NS times 0..T-1 of ONE env (index ``env`` of the batch: heterogeneous cases
+    give every env its own rules) stepped from a reset (stepping past episode ends: the parameters
+    keep evolving with t): prob [T, S, A, D] + the time-invariant part."""
+    n = env + 1
+    actions = harness.draw_actions(case, seed + 1, T, n)
+    clock, per_env, _, _ = harness.make_streams(seed, n, T + 1, n_slots_of(case))
+    envs = builder(case, n, per_env)
     vec = vector.SyncVector(envs, per_env, clock, autoreset=False)
     vec.reset(k=0)
     probs, last = [], None
     for t in range(T):
         vec.step(actions[t], k=t + 1)
-        last = table_of(envs[0])
+        last = table_of(envs[env])
         probs.append(last["prob"])
     return {"prob": np.stack(probs), "next": last["next"], "reward": last["reward"], "done": last["done"]}
 

@@ -44,3 +44,13 @@ def test_tables_match_golden(name):
 def test_table_rows_are_distributions():
     tab = _gpu_table(CASES["c5_bridge_split"], 30)
     np.testing.assert_allclose(tab["prob"].sum(-1), 1.0, atol=1e-12)
+
+
+@pytest.mark.parametrize("name,env", [("c4_frozenlake8_rows", 3), ("c4_frozenlake8_rows", 6), ("het_bridge_split", 2)])
+def test_tables_of_a_heterogeneous_batch_follow_the_env_rows(name, env):
+    T = 50
+    ref = pu.oracle_table_trace(harness.port_envs, CASES[name], T, env=env)
+    genv = pu.gpu_env(CASES[name], 8, autoreset="none")
+    genv.reset(seed=1)
+    got = {k: v.cpu().numpy() for k, v in genv.transition_table(T=T, env=env).items()}
+    _check(ref, got, f"{name}[{env}]")
