@@ -1,0 +1,103 @@
+"""GPU: explicit resets through the C ABI (nsgym_reset): masked resets touch only the selected envs
+(NSWrapper.reset per env, base.py:365-431), persistent parameters survive, cursors rewind."""
+import numpy as np
+import pytest
+
+from tests.cases import CASES
+
+pytestmark = pytest.mark.gpu
+
+
+def _env(name, n, **kw):
+    from tests import parity_util as pu
+
+    case = dict(CASES[name])
+    case["wrapper"] = {**case["wrapper"], **kw.pop("wrapper", {})}
+    env = pu.gpu_env(case, n, **kw)
+    env.reset(seed=4)
+    return env
+
+
+def _step(env, k):
+    for _ in range(k):
+        env.step(env.action_space.sample())
+
+
+@pytest.mark.parametrize("name", ["c1_cartpole_readme", "cartpole_lists", "c3_pendulum", "c2_frozenlake8_drift",
+                                  "bridge_stepwise", "c4_cartpole_rows", "het_cartpole_wide"])
+def test_masked_reset_touches_only_the_selected_envs(name):
+    import torch
+
+    n = 96
+    env = _env(name, n, autoreset="none")
+    _step(env, 7)
+    before = {k: v.clone() for k, v in env.buffers.items() if v is not None}
+    mask = torch.zeros(n, dtype=torch.bool, device=env.device)
+    mask[::3] = True
+    obs, info = env.reset(mask=mask)
+    after = env.buffers
+    keep = ~mask
+    for key in ("state", "t"):
+        assert torch.equal(after[key][keep], before[key][keep]), f"{name}: {key} of an unselected env changed"
+    assert torch.equal(after["theta"][:, keep], before["theta"][:, keep])
+    if after["istate"] is not None:
+        assert torch.equal(after["istate"][:, keep], before["istate"][:, keep])
+    # selected envs: t = 0, parameters and cursors back to their initial values
+    assert int((after["t"][mask] & 0x0FFFFFFF).abs().sum()) == 0
+    fresh = _env(name, n, autoreset="none")
+    if env.program.is_grid and env.program.env_kind != 7:
+        # FrozenLake / CliffWalking: the sampling table stays stale until the next fire (toy_text.py:
+        # 365-367, 395-398), the wrapper's transition_prob is back to the initial distribution
+        assert torch.equal(env.transition_prob()["P"][:, mask], fresh.transition_prob()["P"][:, mask])
+        assert torch.equal(after["theta"][:, mask], before["theta"][:, mask])
+    else:
+        assert torch.equal(after["theta"][:, mask], fresh.buffers["theta"][:, mask])
+    if after["istate"] is not None:
+        assert torch.equal(after["istate"][:, mask], fresh.buffers["istate"][:, mask])
+    assert bool((after["flags"][mask] == 4).all())                       # NSGYM_FLAG_RESET
+    if not env.program.is_grid:                                          # a new initial state was drawn
+        assert not torch.equal(after["state"][mask], before["state"][mask])
+    # and the batch keeps stepping
+    _step(env, 3)
+    assert bool(((env.relative_time() == 3) == mask).all())
+
+
+def test_masked_reset_with_persistent_params_keeps_theta_and_cursors():
+    import torch
+
+    n = 64
+    env = _env("cartpole_persistent", n, autoreset="none")
+    _step(env, 9)
+    before = {k: v.clone() for k, v in env.buffers.items() if v is not None}
+    mask = torch.arange(n, device=env.device) % 2 == 0
+    env.reset(mask=mask)
+    assert torch.equal(env.buffers["theta"], before["theta"])            # base.py:392-395
+    assert torch.equal(env.buffers["istate"], before["istate"])
+    assert int((env.buffers["t"][mask] & 0x0FFFFFFF).abs().sum()) == 0
+    assert torch.equal(env.buffers["t"][~mask], before["t"][~mask])
+
+
+def test_first_reset_must_cover_the_batch():
+    import torch
+
+    import ns_gym_b200.schedulers as PS
+    import ns_gym_b200.update_functions as PU
+    from ns_gym_b200 import native as nv
+    from ns_gym_b200.vector_env import NSVectorEnv
+
+    env = NSVectorEnv("CartPole-v1", {"masspole": PU.IncrementUpdate(PS.ContinuousScheduler(), k=0.1)}, 32)
+    with pytest.raises(nv.NsgymError):
+        env.step_raw(torch.zeros(32, dtype=torch.int32, device=env.device))       # step before reset
+    with pytest.raises(nv.NsgymError):
+        env.reset(mask=torch.ones(32, dtype=torch.bool, device=env.device))       # first reset needs all envs
+    env.reset(seed=1)
+    env.step_raw(torch.zeros(32, dtype=torch.int32, device=env.device))
+
+
+def test_seeded_resets_replay_and_differ_across_seeds():
+    import torch
+
+    a, b, c = (_env("c1_cartpole_readme", 256, precision="fp32") for _ in range(3))
+    a.reset(seed=10); b.reset(seed=10); c.reset(seed=11)
+    assert torch.equal(a.buffers["state"], b.buffers["state"])
+    assert not torch.equal(a.buffers["state"], c.buffers["state"])
