@@ -10,11 +10,6 @@
 
 namespace nsg {
 
-inline bool is_fast_affine(int op) {
-  return op == NSGYM_UPD_NOP || op == NSGYM_UPD_ADD || op == NSGYM_UPD_ADD_T || op == NSGYM_UPD_MUL ||
-         op == NSGYM_UPD_RW;
-}
-
 template <typename R> struct TrueMin;
 template <> struct TrueMin<float> { static constexpr float value = 1.401298464324817e-45f; };
 template <> struct TrueMin<double> { static constexpr double value = 4.9406564584124654e-324; };
