@@ -1,9 +1,11 @@
 """Build ``libnsgym_b200.so`` in-tree with nvcc for sm_100a (cross-compiles without a GPU).
 
-Five translation units, compiled in parallel:
+Fifteen translation units, compiled in parallel:
 
-* ``nsgym_f32.cu``        fp32 fast-mode classic-control kernels (FMA contraction on)
-* ``nsgym_f64.cu``        fp64 parity-mode kernels, ``-fmad=false`` (NumPy rounds every op)
+* ``nsgym_classic_kind.cu``  x 10: the classic-control kernels of one env kind in one precision
+                          (fp32 fast mode with FMA contraction; fp64 parity mode with ``-fmad=false``:
+                          NumPy rounds every op)
+* ``nsgym_f32.cu`` / ``nsgym_f64.cu``  dispatch over the kinds + the known-answer evaluation kernels
 * ``nsgym_gridworld.cu``  gridworld kernels, ``-fmad=false`` (fp64 cumulative sums / W1)
 * ``nsgym_rows.cu``       lowering of per-env rows (heterogeneous batches, host code)
 * ``nsgym_abi.cu``        the C ABI (host code)
@@ -28,13 +30,19 @@ OBJ_DIR = os.path.join(LIB_DIR, "obj")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-I", INCLUDE, "-I", CSRC,
           "--expt-relaxed-constexpr"]
+# object name -> (source, extra flags).  The classic-control kernels build as one unit per
+# (precision, env kind): ten units in parallel instead of two long ones.
 UNITS = {
-    "nsgym_f32.cu": [],
-    "nsgym_f64.cu": ["-fmad=false"],
-    "nsgym_gridworld.cu": ["-fmad=false"],
-    "nsgym_rows.cu": [],
-    "nsgym_abi.cu": [],
+    "nsgym_f32.o": ("nsgym_f32.cu", []),
+    "nsgym_f64.o": ("nsgym_f64.cu", ["-fmad=false"]),
+    "nsgym_gridworld.o": ("nsgym_gridworld.cu", ["-fmad=false"]),
+    "nsgym_rows.o": ("nsgym_rows.cu", []),
+    "nsgym_abi.o": ("nsgym_abi.cu", []),
 }
+for _kind in range(5):
+    UNITS[f"nsgym_kind{_kind}_f32.o"] = ("nsgym_classic_kind.cu", [f"-DNSGYM_TU_KIND={_kind}", "-DNSGYM_TU_REAL=float"])
+    UNITS[f"nsgym_kind{_kind}_f64.o"] = ("nsgym_classic_kind.cu",
+                                         [f"-DNSGYM_TU_KIND={_kind}", "-DNSGYM_TU_REAL=double", "-fmad=false"])
 
 
 def _nvcc() -> str:
@@ -79,8 +87,8 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
     os.makedirs(obj_dir, exist_ok=True)
 
     def compile_unit(item):
-        name, extra = item
-        obj = os.path.join(obj_dir, name.replace(".cu", ".o"))
+        obj_name, (name, extra) = item
+        obj = os.path.join(obj_dir, obj_name)
         cmd = [nvcc, *ARCH, *COMMON, *extra, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, name), "-o", obj]
         if ptxas_info:
             cmd[1:1] = ["-Xptxas", "-v"]
@@ -91,8 +99,10 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
             sys.stderr.write(r.stderr)
         return obj
 
-    with ThreadPoolExecutor(max_workers=len(UNITS)) as pool:
-        objs = list(pool.map(compile_unit, UNITS.items()))
+    # longest units first; one nvcc per core
+    order = sorted(UNITS.items(), key=lambda kv: (0 if "kind" in kv[0] else 1, kv[0]))
+    with ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 4)) as pool:
+        objs = list(pool.map(compile_unit, order))
     link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", lib_path, *objs]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:

@@ -274,6 +274,14 @@ static cudaError_t launch_classic_np(std::integer_sequence<int, NP...>, LaunchOp
   return e;
 }
 
+// One translation unit per (precision, env kind) -- nsgym_classic_kind.cu compiled with
+// -DNSGYM_TU_REAL / -DNSGYM_TU_KIND -- holds the kernels of that kind; the dispatchers in
+// nsgym_f32.cu / nsgym_f64.cu only see this declaration.
+template <typename R, int KIND>
+cudaError_t launch_classic_kind(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& a,
+                                cudaStream_t stream);
+
+#ifdef NSGYM_TU_KIND
 template <typename R, int KIND>
 static cudaError_t launch_classic_k(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,
                                     const LaunchIO& a, cudaStream_t stream) {
@@ -281,16 +289,23 @@ static cudaError_t launch_classic_k(LaunchOp op, const NsgymSpec& spec, const De
                                     stream);
 }
 
+template <typename R, int KIND>
+cudaError_t launch_classic_kind(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& a,
+                                cudaStream_t stream) {
+  return launch_classic_k<R, KIND>(op, spec, pools, a, stream);
+}
+#endif  // NSGYM_TU_KIND
+
 template <typename R>
 static cudaError_t launch_classic_t(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,
                                     const LaunchIO& a, cudaStream_t stream) {
   switch (spec.env_kind) {
-    case NSGYM_ENV_CARTPOLE: return launch_classic_k<R, NSGYM_ENV_CARTPOLE>(op, spec, pools, a, stream);
-    case NSGYM_ENV_ACROBOT: return launch_classic_k<R, NSGYM_ENV_ACROBOT>(op, spec, pools, a, stream);
-    case NSGYM_ENV_MOUNTAINCAR: return launch_classic_k<R, NSGYM_ENV_MOUNTAINCAR>(op, spec, pools, a, stream);
+    case NSGYM_ENV_CARTPOLE: return launch_classic_kind<R, NSGYM_ENV_CARTPOLE>(op, spec, pools, a, stream);
+    case NSGYM_ENV_ACROBOT: return launch_classic_kind<R, NSGYM_ENV_ACROBOT>(op, spec, pools, a, stream);
+    case NSGYM_ENV_MOUNTAINCAR: return launch_classic_kind<R, NSGYM_ENV_MOUNTAINCAR>(op, spec, pools, a, stream);
     case NSGYM_ENV_MOUNTAINCAR_CONT:
-      return launch_classic_k<R, NSGYM_ENV_MOUNTAINCAR_CONT>(op, spec, pools, a, stream);
-    case NSGYM_ENV_PENDULUM: return launch_classic_k<R, NSGYM_ENV_PENDULUM>(op, spec, pools, a, stream);
+      return launch_classic_kind<R, NSGYM_ENV_MOUNTAINCAR_CONT>(op, spec, pools, a, stream);
+    case NSGYM_ENV_PENDULUM: return launch_classic_kind<R, NSGYM_ENV_PENDULUM>(op, spec, pools, a, stream);
     default: return cudaErrorInvalidValue;
   }
 }
