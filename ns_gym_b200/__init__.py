@@ -10,7 +10,7 @@ from . import base, schedulers, update_functions  # noqa: F401
 
 __version__ = "0.1.0"
 
-_LAZY = {"compile", "native", "vector_env", "wrappers", "distributed", "build", "spaces"}
+_LAZY = {"compile", "native", "vector_env", "wrappers", "distributed", "build", "spaces", "utils"}
 
 
 def make(env_id: str, num_envs: int = 1, **kwargs):

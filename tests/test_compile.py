@@ -187,3 +187,17 @@ def test_heterogeneous_cases_compile_per_env():
                                   precision="fp64", **c["wrapper"], **c["make"])
         assert rows.shape == (12, prog.spec.n_slots)
         assert len({tuple(r) for r in rows["upd_op"].tolist()}) > 1, f"{name}: rows are all alike"
+
+
+def test_type_mismatch_checker_matches_the_reference_helper():
+    """ns_gym/utils.py:122-152."""
+    from ns_gym_b200.base import Reward
+    from ns_gym_b200.utils import type_mismatch_checker
+
+    obs = {"state": [1, 2], "env_change": {}, "delta_change": {}, "relative_time": 3}
+    rew = Reward(reward=1.5, env_change={}, delta_change={}, relative_time=3)
+    assert type_mismatch_checker(obs, rew) == ([1, 2], 1.5)
+    assert type_mismatch_checker([1, 2], 0.5) == ([1, 2], 0.5)
+    assert type_mismatch_checker() == (None, None)
+    with pytest.raises(AssertionError):
+        type_mismatch_checker({"not_state": 1}, None)
