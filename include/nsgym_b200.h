@@ -233,6 +233,14 @@ int nsgym_reset(NsgymHandle* h, const uint8_t* d_mask, const double* d_inj_unifo
 int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform,
                const double* d_inj_normal, int skip_updates, void* stream);
 
+/* Result packaging of NSWrapper.step (base.py:314-361) for the batch, in one launch: splits the
+ * flag / change-mask / time words the step left in the bound buffers into what the wrapper
+ * returns -- d_terminated, d_truncated, d_was_reset uint8[N] (0 / 1), d_relative_time int32[N],
+ * d_env_change uint8[n_slots][N] (ground-truth env_change of every bound parameter).  Any
+ * pointer may be NULL; byte arrays must be 4-byte aligned, d_relative_time 16-byte aligned. */
+int nsgym_unpack(NsgymHandle* h, uint8_t* d_terminated, uint8_t* d_truncated, uint8_t* d_was_reset,
+                 int32_t* d_relative_time, uint8_t* d_env_change, void* stream);
+
 /* Same call with HOST buffers: copies actions host->device, steps, copies the requested
  * results device->host, in `n_chunks` pipelined chunks, and returns after the last copy has
  * completed (synchronous).  This is the end-to-end call a host-side agent loop makes. */

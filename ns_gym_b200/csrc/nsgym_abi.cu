@@ -200,6 +200,48 @@ __global__ void fill_planes_kernel(uint32_t* __restrict__ dst, uint32_t n_dst, u
   }
 }
 
+// NSWrapper.step packaging (base.py:314-361): flags / change mask / time word -> per-field arrays.
+// Four envs per thread: 32-bit accesses to the byte arrays, 128-bit accesses to the time words
+// (torch allocations are 256-byte aligned and every plane offset j * n keeps 4-byte alignment
+// when n is a multiple of 4; other batch sizes take the scalar tail path for every env).
+__device__ __forceinline__ void unpack_one(uint32_t f, uint32_t c, int32_t tw, uint32_t i, uint32_t n, int n_slots,
+                                           uint8_t* terminated, uint8_t* truncated, uint8_t* was_reset,
+                                           int32_t* rel_time, uint8_t* env_change) {
+  if (terminated) terminated[i] = (f & NSGYM_FLAG_TERMINATED) ? 1 : 0;
+  if (truncated) truncated[i] = (f & NSGYM_FLAG_TRUNCATED) ? 1 : 0;
+  if (was_reset) was_reset[i] = (f & NSGYM_FLAG_RESET) ? 1 : 0;
+  if (rel_time) rel_time[i] = tw & 0x0FFFFFFF;
+  if (env_change)
+    for (int j = 0; j < n_slots; ++j) env_change[uint32_t(j) * n + i] = (c >> j) & 1u;
+}
+
+__global__ void __launch_bounds__(256)
+unpack_kernel(const uint8_t* __restrict__ flags, const uint8_t* __restrict__ change, const int32_t* __restrict__ t,
+              uint32_t n, int n_slots, uint8_t* __restrict__ terminated, uint8_t* __restrict__ truncated,
+              uint8_t* __restrict__ was_reset, int32_t* __restrict__ rel_time, uint8_t* __restrict__ env_change) {
+  const uint32_t q = blockIdx.x * blockDim.x + threadIdx.x;      // group of four envs
+  const uint32_t i0 = q * 4;
+  if (i0 >= n) return;
+  if ((n & 3u) == 0) {
+    const uint32_t f4 = reinterpret_cast<const uint32_t*>(flags)[q];
+    const uint32_t c4 = reinterpret_cast<const uint32_t*>(change)[q];
+    const int4 t4 = reinterpret_cast<const int4*>(t)[q];
+    // bit k of byte b of f4 -> byte b of the result, as 0 / 1
+    if (terminated) reinterpret_cast<uint32_t*>(terminated)[q] = f4 & 0x01010101u;
+    if (truncated) reinterpret_cast<uint32_t*>(truncated)[q] = (f4 >> 1) & 0x01010101u;
+    if (was_reset) reinterpret_cast<uint32_t*>(was_reset)[q] = (f4 >> 2) & 0x01010101u;
+    if (rel_time)
+      reinterpret_cast<int4*>(rel_time)[q] = make_int4(t4.x & 0x0FFFFFFF, t4.y & 0x0FFFFFFF, t4.z & 0x0FFFFFFF,
+                                                       t4.w & 0x0FFFFFFF);
+    if (env_change)
+      for (int j = 0; j < n_slots; ++j)
+        reinterpret_cast<uint32_t*>(env_change + size_t(j) * n)[q] = (c4 >> j) & 0x01010101u;
+    return;
+  }
+  for (uint32_t i = i0; i < n && i < i0 + 4; ++i)
+    unpack_one(flags[i], change[i], t[i], i, n, n_slots, terminated, truncated, was_reset, rel_time, env_change);
+}
+
 inline unsigned blocks_for(uint64_t n) { return unsigned((n + 255) / 256); }
 
 }  // namespace
@@ -353,6 +395,18 @@ int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform
   if (e != cudaSuccess) return fail(-10, "step launch: %s", cudaGetErrorString(e));
   h->step_index += 1;
   if (h->plan_elapsed >= 0) h->plan_elapsed += 1;
+  return 0;
+}
+
+int nsgym_unpack(NsgymHandle* h, uint8_t* d_terminated, uint8_t* d_truncated, uint8_t* d_was_reset,
+                 int32_t* d_relative_time, uint8_t* d_env_change, void* stream) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  const uint32_t n = uint32_t(h->spec.n_envs);
+  unpack_kernel<<<blocks_for((uint64_t(n) + 3) / 4), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->buf.d_flags, h->buf.d_change, h->buf.d_t, n, h->spec.n_slots, d_terminated, d_truncated, d_was_reset,
+      d_relative_time, d_env_change);
+  NSG_CUDA(cudaGetLastError());
+  h->launches += 1;
   return 0;
 }
 

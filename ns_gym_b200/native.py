@@ -91,7 +91,7 @@ class NsgymHostOut(C.Structure):
 
 EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
-    "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_step_host",
+    "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_unpack", "nsgym_step_host",
     "nsgym_rollout", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
     "nsgym_launch_count",
 ]
@@ -137,6 +137,7 @@ def load(build_if_missing: bool = False):
     lib.nsgym_bind.argtypes = [C.c_void_p, C.POINTER(NsgymBuffers)]
     lib.nsgym_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsgym_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.nsgym_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsgym_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymHostOut), C.c_int]
     lib.nsgym_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p]

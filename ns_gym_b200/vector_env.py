@@ -25,6 +25,20 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+class _LazyInfo(dict):
+    """``info`` dict whose expensive entries (callables) are evaluated on first access."""
+
+    def __getitem__(self, key):
+        v = dict.__getitem__(self, key)
+        if callable(v):
+            v = v()
+            dict.__setitem__(self, key, v)
+        return v
+
+    def get(self, key, default=None):
+        return self[key] if key in self else default
+
+
 class NSVectorEnv:
     def __init__(self, env_id: str, tunable_params: dict, num_envs: int, *,
                  change_notification: bool = False, delta_change_notification: bool = False,
@@ -152,6 +166,13 @@ class NSVectorEnv:
             nv.check(self.lib.nsgym_bind(self._h, C.byref(cb)), "nsgym_bind")
         self._zeros_u8 = torch.zeros(n, dtype=torch.uint8, device=self.device)
         self._zeros_real = torch.zeros(n, dtype=self.real, device=self.device)
+        # result packaging (nsgym_unpack): written by ONE launch per step and handed out as they are --
+        # the tensors a step returns are valid until the next step of this batch
+        self._terminated = torch.zeros(n, dtype=torch.bool, device=self.device)
+        self._truncated = torch.zeros(n, dtype=torch.bool, device=self.device)
+        self._was_reset = torch.zeros(n, dtype=torch.bool, device=self.device)
+        self._rel_time = torch.zeros(n, dtype=torch.int32, device=self.device)
+        self._env_change = torch.zeros((max(len(self.keys), 1), n), dtype=torch.uint8, device=self.device)
 
     def to_storage(self, x):
         """Reorder a per-env array / tensor from the caller's env order to storage order."""
@@ -278,30 +299,31 @@ class NSVectorEnv:
 
     def _package(self):
         b = self.buffers
-        flags = b["flags"]
-        terminated = (flags & nv.FLAG_TERMINATED) != 0
-        truncated = (flags & nv.FLAG_TRUNCATED) != 0
+        with torch.cuda.device(self.device):
+            nv.check(self.lib.nsgym_unpack(self._h, _ptr(self._terminated), _ptr(self._truncated),
+                                           _ptr(self._was_reset), _ptr(self._rel_time), _ptr(self._env_change),
+                                           self._stream()), "nsgym_unpack")
         muted = self.frozen or (self.is_sim_env and not self.in_sim_change)
-        gt_c = self.ground_truth_change()
+        gt_c = {k: self._env_change[j] for j, k in enumerate(self.keys)}
         gt_d = self.ground_truth_delta()
         zc = {k: self._zeros_u8 for k in self.keys}
         zd = {k: self._zeros_real for k in self.keys}
         env_change = zc if (not self.change_notification or muted) else gt_c
         delta_change = zd if (not self.delta_change_notification or muted) else gt_d
-        rel = self.relative_time()
+        rel = self._rel_time
         obs = {"state": self.observation(), "env_change": env_change, "delta_change": delta_change,
                "relative_time": rel}
         reward: Any = b["reward"]
         if not self.scalar_reward:
             reward = Reward(reward=b["reward"], env_change=env_change, delta_change=delta_change,
                             relative_time=rel)
-        info = {"Ground Truth Env Change": gt_c, "Ground Truth Delta Change": gt_d,
-                "was_reset": (flags & nv.FLAG_RESET) != 0}
+        info = _LazyInfo({"Ground Truth Env Change": gt_c, "Ground Truth Delta Change": gt_d,
+                          "was_reset": self._was_reset})
         if self.program.is_grid:
-            info["transition_prob"] = self.transition_prob()
+            info["transition_prob"] = self.transition_prob      # evaluated on first access
         else:
             info["prob"] = 1.0                                   # classic_control.py:98
-        return obs, reward, terminated, truncated, info
+        return obs, reward, self._terminated, self._truncated, info
 
     # ---- parameter views ----
     def theta(self) -> dict:
