@@ -301,6 +301,13 @@ int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_
                       const double* d_inj_uniform, const double* d_inj_normal, int64_t n,
                       void* stream);
 
+/* replaces: ns_gym/utils.py:55-94 (wasserstein_distance on indices) as the step kernels compute it
+ * for delta_change (base.py:192-203): d_u, d_v are double[dim][n] (dim 3 or 4); d_out[n] = the
+ * kernels' value (quotients through one shared reciprocal refinement per divisor), d_ref[n] = the
+ * same sum with plain IEEE divisions.  Test entry: the two must agree bit for bit. */
+int nsgym_eval_w1(int dim, const double* d_u, const double* d_v, double* d_out, double* d_ref,
+                  int64_t n, void* stream);
+
 /* Handle options.  NSGYM_OPT_GENERAL_KERNELS != 0: always launch the general kernel instantiations
  * (all rule classes, injection-capable) instead of the lean ones the library would pick for this
  * program -- same results (bit for bit in fp64 mode), used by the tests to tie the lean kernels to

@@ -629,6 +629,15 @@ int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_
   return 0;
 }
 
+int nsgym_eval_w1(int dim, const double* d_u, const double* d_v, double* d_out, double* d_ref, int64_t n,
+                  void* stream) {
+  if (!d_u || !d_v || !d_out || !d_ref || n < 0) return fail(-1, "bad argument");
+  if (dim != 3 && dim != 4) return fail(-1, "dim must be 3 or 4");
+  const cudaError_t e = nsg::launch_eval_w1(dim, d_u, d_v, d_out, d_ref, n, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-10, "eval_w1 launch: %s", cudaGetErrorString(e));
+  return 0;
+}
+
 int nsgym_set_option(NsgymHandle* h, int option, int64_t value) {
   if (!h) return fail(-1, "NULL handle");
   switch (option) {

@@ -44,13 +44,21 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
                                  cudaStream_t stream) {
   if (spec.n_slots > MAXP || spec.n_dist != D) return cudaErrorInvalidValue;
   const GridProgram<MAXP> G = build_grid_program<MAXP>(spec, pools);
+  // lean instantiation when every bound rule is deterministic
+  bool slow = a.general_kernels != 0 || a.inj_u != nullptr;     // the lean kernels fold the injection tests away
+  for (int j = 0; j < spec.n_slots; ++j) {
+    const NsgymSlot& sl = spec.slots[j];
+    slow |= sl.sched_op == NSGYM_SCHED_RANDOM || sl.sched_op == NSGYM_SCHED_DECAY ||
+            sl.sched_op == NSGYM_SCHED_MEMORYLESS || sl.upd_op == NSGYM_UPD_D_RANDOM || sl.ui[2] != 0;
+  }
+  const bool het = a.rows && a.rows->active;
   LaunchIO a2 = a;
-  a2.prefetch = 1;
+  a2.prefetch = 1;       // Philox block 0 before any divergent branch (the lean Bridge step kernel ignores it)
   const StepIO<double> io = build_io<double>(a2);
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
-  if (a.rows && a.rows->active) {
+  if (het) {
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     switch (op) {
       case OP_STEP:
@@ -65,14 +73,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     }
     return cudaGetLastError();
   }
-  // lean instantiation when every bound rule is deterministic
   const HetT<double, MAXP> no_rows{};
-  bool slow = a.general_kernels != 0 || a.inj_u != nullptr;     // the lean kernels fold the injection tests away
-  for (int j = 0; j < spec.n_slots; ++j) {
-    const NsgymSlot& sl = spec.slots[j];
-    slow |= sl.sched_op == NSGYM_SCHED_RANDOM || sl.sched_op == NSGYM_SCHED_DECAY ||
-            sl.sched_op == NSGYM_SCHED_MEMORYLESS || sl.upd_op == NSGYM_UPD_D_RANDOM || sl.ui[2] != 0;
-  }
   switch (op) {
     case OP_STEP:
       if (slow) grid_step_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, io);
@@ -156,6 +157,16 @@ cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, in
     eval_dist_update_kernel<4><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
   else
     eval_dist_update_kernel<3><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval_w1(int dim, const double* u, const double* v, double* out, double* ref, int64_t n,
+                           cudaStream_t stream) {
+  const unsigned grid = unsigned((n + 255) / 256);
+  if (grid == 0) return cudaSuccess;
+  if (dim == 3) eval_w1_kernel<3><<<grid, 256, 0, stream>>>(u, v, out, ref, uint32_t(n));
+  else if (dim == 4) eval_w1_kernel<4><<<grid, 256, 0, stream>>>(u, v, out, ref, uint32_t(n));
+  else return cudaErrorInvalidValue;
   return cudaGetLastError();
 }
 

@@ -67,6 +67,8 @@ cudaError_t launch_eval_scalar_f64(const NsgymSpec& spec, const DevicePools& poo
                                    const int32_t* time, int32_t* istate, uint8_t* flag, void* delta,
                                    const double* inj_u, const double* inj_z, int64_t n, uint64_t seed,
                                    uint64_t step_index, cudaStream_t stream);
+cudaError_t launch_eval_w1(int dim, const double* u, const double* v, double* out, double* ref, int64_t n,
+                           cudaStream_t stream);
 cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, int slot, double* param,
                              const int32_t* time, int32_t* istate, uint8_t* flag, double* delta,
                              const double* inj_u, int64_t n, uint64_t seed, uint64_t step_index,

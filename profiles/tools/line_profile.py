@@ -14,7 +14,10 @@ from collections import defaultdict
 
 
 def ncu_sass(report):
-    raw = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+    if report.endswith(".csv"):      # page exported on the GPU box: ncu -i rep --page source --csv > file
+        raw = open(report).read()
+    else:
+        raw = subprocess.run(["ncu", "-i", report, "--page", "source", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr = rows[1]
     i_src, i_inst, i_thr = hdr.index("Source"), hdr.index("Instructions Executed"), hdr.index("Thread Instructions Executed")
