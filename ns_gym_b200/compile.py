@@ -407,6 +407,8 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
     spec.env_kind = kind
     spec.precision = {"fp32": nv.F32, "fp64": nv.F64}[precision] if not is_grid else nv.F64
     spec.autoreset = {"none": nv.AUTORESET_NONE, "next_step": nv.AUTORESET_NEXT_STEP}[autoreset]
+    if not 0 < int(n_envs) <= (1 << 28):
+        raise CompileError(f"n_envs must be in 1 .. 2^28 per handle (got {n_envs}): shard larger batches over handles")
     spec.n_envs = int(n_envs)
     spec.env_id_offset = int(env_id_offset)
     spec.seed = int(seed) & (2**64 - 1)

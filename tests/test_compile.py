@@ -201,3 +201,16 @@ def test_type_mismatch_checker_matches_the_reference_helper():
     assert type_mismatch_checker() == (None, None)
     with pytest.raises(AssertionError):
         type_mismatch_checker({"not_state": 1}, None)
+
+
+def test_batch_size_limits():
+    """empty and oversized batches fail at compile time, like nsgym_create does (status -1)"""
+    from ns_gym_b200.compile import CompileError, compile_program, compile_rows
+
+    for n in (0, -1, (1 << 28) + 1):
+        with pytest.raises(CompileError):
+            compile_program("CartPole-v1", {}, n)
+    with pytest.raises(CompileError):
+        compile_rows("CartPole-v1", [])
+    assert compile_program("CartPole-v1", {}, 1).spec.n_envs == 1
+    assert compile_program("CartPole-v1", {}, 1 << 28).spec.n_envs == 1 << 28

@@ -1,13 +1,8 @@
 set -x
-cap() {  # workload, kernel regex
-  W=$1; K=$2
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -s 5 -f -o /tmp/prof_$W python bench.py --workload $W --steps 6 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_$W.log 2>&1
-  python profiles/summarize.py full /tmp/prof_$W.ncu-rep > gpurun_out/full_$W.txt 2>&1
-  ncu -i /tmp/prof_$W.ncu-rep --page source --csv > gpurun_out/sass_$W.csv 2>/dev/null
-}
-for W in c5_bridge c5_bridge_rollout32; do
-  python bench.py --workload $W --steps 200 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/r1e_bench_$W.log 2>&1
-  NSGYM_B200_LIB=$PWD/ns_gym_b200/_lib/libnsgym_b200_mb6.so python bench.py --workload $W --steps 200 --warmup 5 --no-cpu-baseline --e2e-steps 2 > gpurun_out/r1e_bench_mb6_$W.log 2>&1
-done
-cap c1_cartpole step_kernel
-grep -H -o '"value": [0-9.e+]*, "unit": "env-steps/s", "n_gpus"' gpurun_out/r1e_bench_*.log
+TR="python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29517"
+timeout 300 $TR bench.py --gpus 8 --steps 200 --warmup 10 > gpurun_out/r1_scale8_c1_cartpole.log 2> gpurun_out/r1_scale8_c1_cartpole.err
+timeout 300 $TR bench.py --gpus 8 --steps 30 --warmup 3 --workload c5_bridge_rollout100 --log2-envs 23 --e2e-steps 3 > gpurun_out/r1_scale8_c5_bridge_rollout100_64m.log 2> gpurun_out/r1_scale8_c5.err
+timeout 300 $TR bench.py --gpus 8 --steps 200 --warmup 10 --workload c4_hetero --log2-envs 21 --e2e-steps 3 > gpurun_out/r1_scale8_c4_hetero_16m.log 2> gpurun_out/r1_scale8_c4.err
+timeout 300 $TR bench.py --gpus 8 --impl reference --steps 3 --warmup 1 > gpurun_out/r1_scale8_reference.log 2>&1
+tail -c 300 gpurun_out/r1_scale8_*.err
+grep -H -o '"value": [0-9.e+]*, "unit": "env-steps/s", "n_gpus": [0-9]*' gpurun_out/r1_scale8_*.log
