@@ -29,11 +29,16 @@ def block(gids, step_index, blk, seed):
 BLK_POLICY = 13
 
 
-def policy_actions(kind, gids, step_index, seed):
+def policy_actions(kind, gids, step_index, seed, precision="fp64"):
     """The rollout kernels' uniform-random policy (nsgym_device.cuh / nsgym_grid.cuh)."""
     if kind == "grid":      # word z of block 0 (words x, y feed the slip draw)
         return (block(gids, step_index, 0, seed)[2] >> np.uint32(30)).astype(np.int32)
-    x = block(gids, step_index, BLK_POLICY, seed)[0]
+    if precision == "fp32":  # the low bytes of block 0's words (the fp32 draws use the top 24 bits)
+        b = block(gids, step_index, 0, seed)
+        x = ((b[0] & np.uint32(0xFF)) | ((b[1] & np.uint32(0xFF)) << np.uint32(8)) |
+             ((b[2] & np.uint32(0xFF)) << np.uint32(16)) | (b[3] << np.uint32(24))).astype(np.uint32)
+    else:
+        x = block(gids, step_index, BLK_POLICY, seed)[0]
     if kind == "cartpole":
         return (x >> np.uint32(31)).astype(np.int32)
     if kind in ("acrobot", "mountaincar"):

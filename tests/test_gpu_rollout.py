@@ -45,7 +45,7 @@ def test_rollout_equals_single_steps(name, kind, precision):
     steps_alive = torch.zeros(n, dtype=torch.int32, device=b.device)
     first = torch.ones(n, dtype=torch.bool, device=b.device)
     for k in range(K):
-        act = philox_np.policy_actions(kind, gids, step0 + k, seed)
+        act = philox_np.policy_actions(kind, gids, step0 + k, seed, precision)
         obs, r, term, trunc, info = b.step(torch.as_tensor(act))
         was_reset = info["was_reset"]
         first &= ~was_reset
