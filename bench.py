@@ -460,6 +460,15 @@ def run_gpu(args):
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": bytes_per_launch_env / per_launch,
                 "kernel_us_per_launch": launch_s * 1e6 / len(shards)}
+    if traffic and not rollout_k:
+        # the measured DRAM rate next to the algorithmic one: gridworld kernels write a distribution
+        # back only when its update fired, so with a rare scheduler (C2) the traffic is well below
+        # SURVEY 8(d)'s figure (which counts theta read + write every step) and frac can exceed 1
+        roofline["dram_gbs_from_traffic"] = traffic / launch_s / 1e9
+        if traffic < 0.9 * bytes_per_launch_env * n_envs:
+            roofline["note"] = ("DRAM traffic is below the algorithmic bytes: unchanged theta planes are not "
+                                "written back (gridworld kernels), so achieved (algorithmic bytes / time) can "
+                                "exceed the copy peak; dram_gbs_from_traffic is the physical rate")
     if len(shards) > 1:
         roofline["note"] = ("heterogeneous batch: one launch per env kind per step; bytes include the per-env row "
                             "words read each step: " +
