@@ -47,6 +47,8 @@ WORKLOADS = {
     "c3_acrobot_fp64": dict(case="c3_acrobot", log2_envs=22, precision="fp64"),
     "c3_mountaincar": dict(case="c3_mountaincar", log2_envs=22, precision="fp32"),
     "c3_pendulum": dict(case="c3_pendulum", log2_envs=22, precision="fp32"),
+    "c3_mountaincar_fp64": dict(case="c3_mountaincar", log2_envs=22, precision="fp64"),
+    "c3_pendulum_fp64": dict(case="c3_pendulum", log2_envs=22, precision="fp64"),
     "c5_bridge": dict(case="c5_bridge_uniform", log2_envs=24, precision="fp64"),
     # C4: heterogeneous batch, per-env opcode rows, half CartPole (fp32) + half FrozenLake 8x8
     # (envs bucketed by opcode signature within the shard; coefficients stay per env)
@@ -417,6 +419,9 @@ def run_gpu(args):
     env, case = build_env(args.workload, n_envs, rank, seed=args.seed)
     shards = list(getattr(env, "shards", [env]))      # C4: one shard (= one kernel launch) per env kind
     dev = shards[0].device
+    if args.general_kernels:        # the general (all rule classes, injection-capable) instantiations
+        for s in shards:
+            s.set_option("general_kernels", 1)
     env.reset(seed=args.seed)
     actions = [random_actions(s, 1234 + rank + 17 * k) for k, s in enumerate(shards)]
     sampler = ClockSampler(local)
@@ -527,6 +532,7 @@ def run_gpu(args):
                 "env_id": "+".join(s.program.env_id for s in shards),
                 "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
                 "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k,
+                "kernels": "general" if args.general_kernels else "lean where the program allows",
                 "parallelism": f"env-shard x{world}, no data-path collective",
                 "l2_policy": f"working set {env.bytes_per_step * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
@@ -560,6 +566,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30, dest="e2e_steps")
     ap.add_argument("--chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--general-kernels", action="store_true", dest="general_kernels",
+                    help="launch the general kernel instantiations instead of the lean ones (kernel experiments)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
