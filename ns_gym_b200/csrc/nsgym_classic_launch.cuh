@@ -61,11 +61,12 @@ static SlotT<R> lower_slot(const NsgymSlot& a, int lane, int64_t t_max = (int64_
     case NSGYM_UPD_MUL: A = a.uf[0]; break;
     case NSGYM_UPD_RW: B = a.uf[0]; Ct = a.uf[3]; b.flags |= SF_NORMAL; break;
     case NSGYM_UPD_LERP: case NSGYM_UPD_MUL_EXP: case NSGYM_UPD_SIGMOID:
-      b.flags |= std::is_same<R, float>::value ? SF_MEDIUM : SF_SLOW_UPD;
+      b.flags |= SF_MEDIUM;
       break;
-    case NSGYM_UPD_ADD_SIN:    // the bounded sine is good for t <= 1e5
-      b.flags |= (std::is_same<R, float>::value && t_max <= 100000) ? SF_MEDIUM : SF_SLOW_UPD;
+    case NSGYM_UPD_ADD_SIN:    // fp32: the bounded sine is good for t <= 1e5; fp64 calls the accurate sin
+      b.flags |= (std::is_same<R, double>::value || t_max <= 100000) ? SF_MEDIUM : SF_SLOW_UPD;
       break;
+    case NSGYM_UPD_D_UNIFORM: b.flags |= SF_SLOW_UPD | SF_D_AFFINE; break;
     default: b.flags |= SF_SLOW_UPD; break;
   }
   b.fa[0] = R(A); b.fa[1] = R(B); b.fa[2] = R(Ct);
@@ -233,14 +234,14 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   }
   const HetT<R, NP> no_rows{};
   // programs without slow-class slots run a lean instantiation (no rule switches compiled in):
-  // level 0 = fast class only, level 1 = + inline medium rules (fp32 fast mode), level 2 = everything
+  // level 0 = fast class only, level 1 = + inline medium rules, level 2 = everything
   // (injected random tables -- parity tests -- also take level 2: the lean kernels fold the
   // "injected?" tests away)
   int level = (P.n_slow > 0 || a.inj_u || a.inj_z || a.general_kernels) ? 2 : 0;
   if (level == 0)
     for (int j = 0; j < NP; ++j)
       if (P.slot[j].flags & SF_MEDIUM) level = 1;
-  constexpr bool kHasMedium = std::is_same<R, float>::value;
+  constexpr bool kHasMedium = true;
   const unsigned lean_grid = unsigned((a.count + block * NSGYM_LEAN_EPT - 1) / (block * NSGYM_LEAN_EPT));
   switch (op) {
     case OP_STEP:

@@ -1,12 +1,3 @@
 set -x
-bash tools/bench_all.sh c3_mountaincar_fp64 c3_pendulum_fp64
-for W in c1_cartpole c5_bridge c1_cartpole_fp64; do echo "== general $W"; python bench.py --workload $W --no-cpu-baseline --e2e-steps 2 --general-kernels | grep -o '"value": [0-9.e+]*, "unit": "env-steps/s", "n_gpus"\|"frac": [0-9.]*'; done
-cap() {  # workload, kernel regex
-  W=$1; K=$2
-  timeout 600 ncu --set full --clock-control none --import-source on -k regex:$K -c 1 -s 60 -f -o /tmp/prof_$W python bench.py --workload $W --steps 70 --warmup 3 --no-cpu-baseline --e2e-steps 1 > gpurun_out/ncu_$W.log 2>&1
-  python profiles/summarize.py full /tmp/prof_$W.ncu-rep > gpurun_out/full_${W}_steady.txt 2>&1
-  ncu -i /tmp/prof_$W.ncu-rep --page source --csv > gpurun_out/sass_${W}_steady.csv 2>/dev/null
-}
-cap c3_pendulum_fp64 step_kernel
-cap c3_mountaincar_fp64 step_kernel
-cap c5_bridge_rollout32 rollout
+python -m pytest tests -m gpu -x -q 2>&1 | tail -3
+bash tools/bench_all.sh c5_bridge c5_bridge_rollout32 c5_bridge_rollout100 c5_bridge_split_rollout32 c4_hetero c2_frozenlake8_16m
