@@ -172,11 +172,13 @@ static HetT<R, NP> build_het(const RowTable& t) {
   return H;
 }
 
-// block 0 of the Philox stream is consumed by next-step autoreset (initial-state draws), by the
-// normals of lanes 0 / 1 and by the gridworld slip draw: compute it once, before any branch
+// block 0 of the Philox stream is consumed by the normals of lanes 0 / 1 and by the gridworld slip
+// draw on every step: compute it once, before any branch.  When only next-step autoreset needs it
+// (initial-state draws of the few lanes that reset), it is computed in the reset branch instead:
+// a warp without a resetting lane -- most warps of MountainCar / Pendulum / Acrobot, whose
+// episodes last hundreds of steps -- skips the ten rounds altogether.
 inline bool wants_prefetch(const NsgymSpec& spec) {
   if (is_grid_kind(spec.env_kind)) return true;
-  if (spec.autoreset == NSGYM_AUTORESET_NEXT_STEP) return true;
   for (int j = 0; j < spec.n_slots; ++j)
     if (slot_draws_block0(spec.slots[j], j)) return true;
   return false;
