@@ -149,6 +149,19 @@ class _Pools:
         return off
 
 
+def _as_contiguous_range(slot: nv.NsgymSlot, times) -> bool:
+    """Strength reduction: an event set whose live part (inside the scheduler's own [start, end]) is
+    one run a, a+1, .., b fires exactly like a ContinuousScheduler on [a, b] -- the kernels' fast
+    class (one unsigned range compare) instead of a bitmap word fetched from the pool.  A single
+    event time (the usual "step change at t*") is the common case."""
+    live = [t for t in times if slot.start <= t <= slot.end]
+    if not live or live[-1] - live[0] + 1 != len(live):
+        return False
+    slot.sched_op = nv.SCHED_CONTINUOUS
+    slot.start, slot.end = live[0], live[-1]
+    return True
+
+
 def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, planes: dict, j: int):
     kind = type(sch).__name__
     slot.start, slot.end = _int_bounds(sch.start, sch.end)
@@ -160,11 +173,12 @@ def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, plane
         slot.sched_op = nv.SCHED_PERIODIC
         slot.si[0] = int(sch.period)
     elif kind == "DiscreteScheduler":
-        times = sorted(int(e) for e in sch.event_list if e == int(e) and e >= 0)
-        n_bits = (times[-1] + 1) if times else 0
-        slot.sched_op = nv.SCHED_BITMAP
-        slot.si[0] = pools.add_bitmap(times, n_bits)
-        slot.si[1] = n_bits
+        times = sorted({int(e) for e in sch.event_list if e == int(e) and e >= 0})
+        if not _as_contiguous_range(slot, times):
+            n_bits = (times[-1] + 1) if times else 0
+            slot.sched_op = nv.SCHED_BITMAP
+            slot.si[0] = pools.add_bitmap(times, n_bits)
+            slot.si[1] = n_bits
     elif kind == "BurstScheduler":
         slot.sched_op = nv.SCHED_BURST
         slot.si[0] = int(sch.on_duration)
@@ -176,9 +190,14 @@ def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, plane
         for ws, we in sch.windows:
             lo, hi = _int_bounds(ws, we)
             flat += [lo, hi]
-        slot.sched_op = nv.SCHED_WINDOW
-        slot.si[0] = pools.add_i(flat)
-        slot.si[1] = len(flat) // 2
+        lo1, hi1 = (max(flat[0], slot.start), min(flat[1], slot.end)) if len(flat) == 2 else (1, 0)
+        if lo1 <= hi1:         # a single window = a Continuous scheduler on it (fast class)
+            slot.sched_op = nv.SCHED_CONTINUOUS
+            slot.start, slot.end = lo1, hi1
+        else:
+            slot.sched_op = nv.SCHED_WINDOW
+            slot.si[0] = pools.add_i(flat)
+            slot.si[1] = len(flat) // 2
     elif kind == "RandomScheduler":
         slot.sched_op = nv.SCHED_RANDOM
         slot.sf[0] = float(sch.probability)
@@ -196,9 +215,10 @@ def _lower_scheduler(sch, slot: nv.NsgymSlot, pools: _Pools, horizon: int, plane
         # the range gate would have called it (base.py:79-81)
         lo, hi = slot.start, min(slot.end, horizon)
         times = [t for t in range(lo, hi + 1) if sch.event_function(t)]
-        slot.sched_op = nv.SCHED_BITMAP
-        slot.si[0] = pools.add_bitmap(times, horizon + 1)
-        slot.si[1] = horizon + 1
+        if not _as_contiguous_range(slot, times):
+            slot.sched_op = nv.SCHED_BITMAP
+            slot.si[0] = pools.add_bitmap(times, horizon + 1)
+            slot.si[1] = horizon + 1
     else:
         raise CompileError(f"scheduler {kind} cannot be compiled")
 

@@ -39,6 +39,14 @@ def test_scheduler_lowering():
     assert s.sched_op == nv.SCHED_BITMAP and s.si[1] == 34
     words = [p.spec.bitmap[i] for i in range(p.spec.n_bitmap_words)]
     assert words == [2, 2]
+    # one run of event times = a Continuous scheduler on that range (fast class, no bitmap)
+    for events, kw, want in (({12}, {}, (12, 12)), ({4, 5, 6}, {}, (4, 6)), ({3, 4, 5}, dict(start=2, end=8), (3, 5))):
+        s = compile_program("CartPole-v1", {"gravity": U.IncrementUpdate(S.DiscreteScheduler(events, **kw), k=1.0)},
+                            4).spec.slots[0]
+        assert (s.sched_op, s.start, s.end) == (nv.SCHED_CONTINUOUS, *want)
+    s = compile_program("CartPole-v1", {"gravity": U.IncrementUpdate(S.WindowScheduler([(3, 7)], start=5), k=1.0)},
+                        4).spec.slots[0]
+    assert (s.sched_op, s.start, s.end) == (nv.SCHED_CONTINUOUS, 5, 7)
     tp = {"gravity": U.IncrementUpdate(S.CustomScheduler(lambda t: t in (0, 499, 500)), k=1.0)}
     p = compile_program("CartPole-v1", tp, 4)                        # horizon = TimeLimit 500
     assert p.spec.slots[0].si[1] == 501
