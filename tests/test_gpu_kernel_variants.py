@@ -51,6 +51,22 @@ def test_lean_kernels_equal_general_kernels_fp64(name):
             assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
 
 
+@pytest.mark.parametrize("name", ["frozenlake8_cyclic_stale", "c2_frozenlake8_stepchange", "bridge_stepwise",
+                                  "c5_bridge_uniform", "cliff_drift"])
+def test_lean_gridworld_kernels_with_persistent_params_fp64(name):
+    """persistent_params=True: a reset keeps distributions and cursors, so the lean kernels (which
+    write a plane back only when its update fired or a reset re-initialised it) store nothing on a
+    reset step -- the general kernels store everything; both must leave identical buffers."""
+    import torch
+
+    case = dict(CASES[name])
+    case["wrapper"] = dict(case.get("wrapper", {}), persistent_params=True)
+    lean, general = _run(case, "fp64", False, steps=60), _run(case, "fp64", True, steps=60)
+    for k, (x, y) in enumerate(zip(lean, general)):
+        for key in x:
+            assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+
+
 @pytest.mark.parametrize("name", [n for n in CASES_UNDER_TEST if "frozenlake" not in n and "bridge" not in n
                                   and "cliff" not in n])
 def test_lean_kernels_track_general_kernels_fp32(name):
