@@ -27,12 +27,14 @@ def block(gids, step_index, blk, seed):
 
 
 BLK_POLICY = 13
+BLK_PAIR = 14
 
 
 def policy_actions(kind, gids, step_index, seed, precision="fp64"):
     """The rollout kernels' uniform-random policy (nsgym_device.cuh / nsgym_grid.cuh)."""
-    if kind == "grid":      # word z of block 0 (words x, y feed the slip draw)
-        return (block(gids, step_index, 0, seed)[2] >> np.uint32(30)).astype(np.int32)
+    if kind == "grid":      # block 14 of the step PAIR, half = step & 1; the two lowest bits of the half's low word
+        w = block(gids, step_index >> 1, BLK_PAIR, seed)
+        return (w[3 if step_index & 1 else 1] & np.uint32(3)).astype(np.int32)
     if precision == "fp32":  # the low bytes of block 0's words (the fp32 draws use the top 24 bits)
         b = block(gids, step_index, 0, seed)
         x = ((b[0] & np.uint32(0xFF)) | ((b[1] & np.uint32(0xFF)) << np.uint32(8)) |
