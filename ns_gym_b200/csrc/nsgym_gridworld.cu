@@ -53,7 +53,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   }
   const bool het = a.rows && a.rows->active;
   LaunchIO a2 = a;
-  a2.prefetch = 1;       // Philox block 0 before any divergent branch (the lean Bridge step kernel ignores it)
+  a2.prefetch = 1;       // the step pair's Philox block before any divergent branch (general kernels; the lean step kernels draw lazily)
   const StepIO<double> io = build_io<double>(a2);
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
