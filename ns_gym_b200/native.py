@@ -122,8 +122,14 @@ def load(build_if_missing: bool = False):
                 f"{path} not found: build the CUDA library first (python -m ns_gym_b200.build or "
                 "__graft_entry__.build()); ns_gym_b200 has no CPU fallback")
     if path == _build.LIB_PATH and not _build.is_current():
-        raise NsgymError(f"{path} is older than the sources under ns_gym_b200/csrc: rebuild it "
-                         "(python -m ns_gym_b200.build or __graft_entry__.build())")
+        # a library older than its sources is never loaded: rebuild it in place (nvcc, ~2 min) unless
+        # told not to; without a toolchain this still fails loudly -- there is no CPU fallback
+        if os.environ.get("NSGYM_B200_NO_AUTOBUILD"):
+            raise NsgymError(f"{path} is older than the sources under ns_gym_b200/csrc: rebuild it "
+                             "(python -m ns_gym_b200.build or __graft_entry__.build())")
+        import sys
+        sys.stderr.write(f"ns_gym_b200: {path} is older than its sources, rebuilding with nvcc ...\n")
+        _build.build_library()
     lib = C.CDLL(path)
     lib.nsgym_abi_version.restype = C.c_int
     lib.nsgym_sizeof.restype = C.c_size_t

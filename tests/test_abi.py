@@ -92,3 +92,20 @@ def test_descriptions_do_not_execute_on_host():
         fn(1.0, 0)
     with pytest.raises(RuntimeError):
         fn.scheduler(0)
+
+
+def test_stale_library_is_never_loaded(monkeypatch):
+    """A library older than its sources is rebuilt (or refused with NSGYM_B200_NO_AUTOBUILD): the
+    kernels that run are the ones in the tree -- and there is no CPU path to fall back to."""
+    from ns_gym_b200 import build, native
+
+    assert build.is_current()
+    monkeypatch.setattr(native, "_lib", None)
+    monkeypatch.setattr(build, "is_current", lambda: False)
+    monkeypatch.setenv("NSGYM_B200_NO_AUTOBUILD", "1")
+    with pytest.raises(native.NsgymError, match="older than the sources"):
+        native.load()
+    rebuilt = []
+    monkeypatch.delenv("NSGYM_B200_NO_AUTOBUILD")
+    monkeypatch.setattr(build, "build_library", lambda *a, **k: rebuilt.append(1) or build.LIB_PATH)
+    assert native.load() is not None and rebuilt == [1]
