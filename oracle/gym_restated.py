@@ -1,14 +1,16 @@
 """Restated gymnasium-1.2.1 base environments (TEST INFRASTRUCTURE -- see oracle/__init__.py).
 
-PARITY STATUS: **UNPINNED**.  gymnasium 1.2.1 (reference ``uv.lock:958-959``) is neither
+PARITY STATUS: **UNPINNED** (except the CartPole step, see below).  gymnasium 1.2.1 (reference ``uv.lock:958-959``) is neither
 vendored in /root/reference nor installed in this image, and no reference test asserts a
 numeric post-step state.  Everything below restates the *published upstream algorithm*
  and is anchored on:
 
 * attribute names the reference reads/writes: ``ns_gym/base.py:611-635`` (ATTRIBUTE_MAP),
   ``ns_gym/wrappers/toy_text.py:51-54,65-69,314-319``;
-* CartPole equations corroborated by the in-tree legacy copy
-  ``ns_gym/benchmark_algorithms/rats-experiments/code/envs/nscartpole_v0.py:92-100``;
+* CartPole equations: PINNED to one ulp against the in-tree legacy copy
+  ``ns_gym/benchmark_algorithms/rats-experiments/code/envs/nscartpole_v0.py:76-135`` (loaded in
+  place by ``tests/golden/make_cartpole_anchor.py``; ``tests/test_oracle_cartpole_anchor.py``
+  checks this module and the CUDA kernel against its 4 096 recorded transitions);
 * default parameter tables ``docs/source/env_pages/classic_control/*.md``;
 * registered episode limits (``ns_gym/__init__.py:17-21`` for Bridge).
 
