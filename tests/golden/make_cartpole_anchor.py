@@ -10,7 +10,7 @@ nscartpole_v0.py:76-135 (`NSCartPoleV0.transition`).  With the cart's tilt switc
 and two actions it is gymnasium's Euler step up to the association of one product
 (`polemass_length * theta_dot * theta_dot` vs `polemass_length * square(theta_dot)`), i.e. to an
 ulp.  The file is loaded IN PLACE with a stub `gym` module; outputs go to
-tests/golden/cartpole_anchor.npz, which travels to the GPU box.
+tests/golden/anchors/cartpole_anchor.npz, which travels to the GPU box.
 """
 import importlib.util
 import os
@@ -20,7 +20,7 @@ import types
 import numpy as np
 
 REF = "/root/reference/ns_gym/benchmark_algorithms/rats-experiments/code/envs/nscartpole_v0.py"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "cartpole_anchor.npz")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), "anchors", "cartpole_anchor.npz")
 N = 4096
 
 

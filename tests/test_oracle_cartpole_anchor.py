@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-GOLDEN = os.path.join(HERE, "golden", "cartpole_anchor.npz")
+GOLDEN = os.path.join(HERE, "golden", "anchors", "cartpole_anchor.npz")
 
 
 def _oracle_step(theta, state, action):
