@@ -359,7 +359,7 @@ def random_actions(env, gen_seed):
     return torch.randint(0, N_ACTIONS[kind], (env.num_envs,), generator=g, device=env.device, dtype=torch.int32)
 
 
-def time_steps(shards, actions, steps, warmup, dist=None, rollout_k=0):
+def time_steps(shards, actions, steps, warmup, dist=None, rollout_k=0, policy=None):
     """W untimed + K timed steps (one launch per shard per step), CUDA events on the launching
     stream; returns seconds."""
     import torch
@@ -369,8 +369,18 @@ def time_steps(shards, actions, steps, warmup, dist=None, rollout_k=0):
         ret = torch.zeros(env.num_envs, dtype=torch.float32, device=env.device)
         length = torch.zeros(env.num_envs, dtype=torch.int32, device=env.device)
 
+        pol = None
+        if policy in ("linear", "linear_per_env"):      # device-side linear / tabular policy, random weights
+            g = torch.Generator(device=env.device)
+            g.manual_seed(4242)
+            shape = env.policy_shape(policy == "linear_per_env")
+            if len(env.policy_shape()) == 1:
+                pol = torch.randint(0, 4, shape, generator=g, device=env.device, dtype=torch.uint8)
+            else:
+                pol = torch.randn(shape, generator=g, device=env.device, dtype=torch.float32)
+
         def launch():
-            env.rollout(rollout_k, 1.0, ret, length)
+            env.rollout(rollout_k, 1.0, ret, length, policy=pol)
     else:
         def launch():
             for s, a in zip(shards, actions):
@@ -433,7 +443,7 @@ def run_gpu(args):
     sampler.mark(0)
     rollout_k = int(wl.get("rollout_k", 0))
     per_launch = max(rollout_k, 1)                     # env-steps each env advances per launch
-    secs = time_steps(shards, actions, args.steps, max(args.warmup, 3), dist, rollout_k)
+    secs = time_steps(shards, actions, args.steps, max(args.warmup, 3), dist, rollout_k, args.rollout_policy)
     launches = env.launch_count - launches0 - max(args.warmup, 3) * len(shards)
     t = torch.tensor([secs], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -531,7 +541,7 @@ def run_gpu(args):
                 "workload": args.workload, "case": wl["case"],
                 "env_id": "+".join(s.program.env_id for s in shards),
                 "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
-                "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k,
+                "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k, "rollout_policy": args.rollout_policy if rollout_k else None,
                 "kernels": "general" if args.general_kernels else "lean where the program allows",
                 "parallelism": f"env-shard x{world}, no data-path collective",
                 "l2_policy": f"working set {env.bytes_per_step * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
@@ -566,6 +576,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30, dest="e2e_steps")
     ap.add_argument("--chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--rollout-policy", default="random", choices=["random", "linear", "linear_per_env"],
+                    dest="rollout_policy", help="device-side policy of the *_rollout* workloads")
     ap.add_argument("--general-kernels", action="store_true", dest="general_kernels",
                     help="launch the general kernel instantiations instead of the lean ones (kernel experiments)")
     args = ap.parse_args()

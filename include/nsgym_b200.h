@@ -256,6 +256,17 @@ int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* ou
 int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d_return,
                   int32_t* d_length, int skip_updates, void* stream);
 
+/* The same fused rollout under a device-side LINEAR policy (shared by the batch, or one per env
+ * when per_env != 0 -- population search evaluates N policies in one launch).
+ * Classic control: d_policy = float[A][O + 1] (row a: O weights, then the bias) per policy, over the
+ * float32 observation of the env kind (O = 4 CartPole, 6 Acrobot, 2 MountainCar(Continuous),
+ * 3 Pendulum); Discrete action spaces take argmax_a (first maximum; A = 2 CartPole, 3 Acrobot /
+ * MountainCar), Box action spaces (A = 1) take the score itself, which the env clips.
+ * Gridworlds: a linear policy on the one-hot cell is a table: d_policy = uint8[nrow * ncol],
+ * action = table[cell].  Steps, flags, autoreset and accumulators as in nsgym_rollout. */
+int nsgym_rollout_linear(NsgymHandle* h, int k_steps, const void* d_policy, int per_env, float gamma,
+                         float* d_return, int32_t* d_length, int skip_updates, void* stream);
+
 /* Planning envs.
  * replaces: get_planning_env + __deepcopy__ (classic_control.py:120-186, toy_text.py:471-511,
  * 669-711) for a batch, with the fan-out MCTS-style consumers need (benchmark_algorithms/MCTS.py:

@@ -481,6 +481,27 @@ int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d
   return 0;
 }
 
+int nsgym_rollout_linear(NsgymHandle* h, int k_steps, const void* d_policy, int per_env, float gamma,
+                         float* d_return, int32_t* d_length, int skip_updates, void* stream) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  if (!h->initialised) return fail(-4, "rollout before reset");
+  if (!d_policy) return fail(-1, "NULL policy (nsgym_rollout runs the uniform-random policy)");
+  if (k_steps <= 0) return fail(-1, "k_steps must be positive");
+  nsg::LaunchIO io = base_io(h);
+  io.k_steps = k_steps;
+  io.gamma = gamma;
+  io.ret = d_return;
+  io.len = d_length;
+  io.skip_updates = skip_updates;
+  io.policy = d_policy;
+  io.policy_per_env = per_env ? 1 : 0;
+  cudaError_t e = dispatch(h, nsg::OP_ROLLOUT, io, static_cast<cudaStream_t>(stream));
+  if (e != cudaSuccess) return fail(-10, "rollout launch: %s", cudaGetErrorString(e));
+  h->step_index += uint64_t(k_steps);
+  if (h->plan_elapsed >= 0) h->plan_elapsed += k_steps;
+  return 0;
+}
+
 int nsgym_fanout(const NsgymHandle* src, NsgymHandle* dst, int fanout, int theta_from_init, void* stream) {
   if (!src || !dst || !src->bound || !dst->bound) return fail(-1, "both handles must be bound");
   if (!src->initialised) return fail(-4, "the source must be reset before a planning copy is taken");

@@ -227,8 +227,8 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
           break;
         case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
         case OP_ROLLOUT:
-          classic_rollout_kernel<R, KIND, NP, 2, true><<<grid, block, 0, stream>>>(P, H, io, a.k_steps, a.gamma, a.ret,
-                                                                                  a.len);
+          classic_rollout_kernel<R, KIND, NP, 2, true><<<grid, block, 0, stream>>>(
+              P, H, io, a.k_steps, a.gamma, a.ret, a.len, static_cast<const float*>(a.policy), a.policy_per_env);
           break;
       }
       return cudaGetLastError();
@@ -239,7 +239,8 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   // level 0 = fast class only, level 1 = + inline medium rules, level 2 = everything
   // (injected random tables -- parity tests -- also take level 2: the lean kernels fold the
   // "injected?" tests away)
-  int level = (P.n_slow > 0 || a.inj_u || a.inj_z || a.general_kernels) ? 2 : 0;
+  // (a linear rollout policy is compiled into the general instantiation only)
+  int level = (P.n_slow > 0 || a.inj_u || a.inj_z || a.general_kernels || (op == OP_ROLLOUT && a.policy)) ? 2 : 0;
   if (level == 0)
     for (int j = 0; j < NP; ++j)
       if (P.slot[j].flags & SF_MEDIUM) level = 1;
@@ -256,7 +257,8 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     case OP_RESET: classic_reset_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io); break;
     case OP_ROLLOUT:
       if (level == 2 || NP == 0)
-        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
+        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len,
+                                                                            static_cast<const float*>(a.policy), a.policy_per_env);
       else if (level == 1) {
         if constexpr (kHasMedium)
           classic_rollout_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);

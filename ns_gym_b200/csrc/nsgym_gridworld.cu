@@ -67,8 +67,12 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
         break;
       case OP_RESET: grid_reset_het_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, H, io); break;
       case OP_ROLLOUT:
-        grid_rollout_kernel<KIND, D, MAXP, true, true><<<grid, block, 0, stream>>>(G, H, io, a.k_steps, a.gamma, a.ret,
-                                                                                  a.len);
+        if (a.policy)
+          grid_rollout_kernel<KIND, D, MAXP, true, true, true><<<grid, block, 0, stream>>>(
+              G, H, io, a.k_steps, a.gamma, a.ret, a.len, static_cast<const uint8_t*>(a.policy), a.policy_per_env);
+        else
+          grid_rollout_kernel<KIND, D, MAXP, true, true><<<grid, block, 0, stream>>>(G, H, io, a.k_steps, a.gamma,
+                                                                                    a.ret, a.len);
         break;
     }
     return cudaGetLastError();
@@ -81,7 +85,10 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
       break;
     case OP_RESET: grid_reset_kernel<KIND, D, MAXP><<<grid, block, 0, stream>>>(G, io); break;
     case OP_ROLLOUT:
-      if (slow) grid_rollout_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
+      if (a.policy)       // tabular policy: the general instantiation
+        grid_rollout_kernel<KIND, D, MAXP, true, false, true><<<grid, block, 0, stream>>>(
+            G, no_rows, io, a.k_steps, a.gamma, a.ret, a.len, static_cast<const uint8_t*>(a.policy), a.policy_per_env);
+      else if (slow) grid_rollout_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
       else grid_rollout_kernel<KIND, D, MAXP, false><<<grid, block, 0, stream>>>(G, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
       break;
   }

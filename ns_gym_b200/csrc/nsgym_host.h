@@ -45,6 +45,7 @@ struct LaunchIO {
   int32_t general_kernels;   // NSGYM_OPT_GENERAL_KERNELS
   // rollout
   int32_t k_steps; float gamma; float* ret; int32_t* len;
+  const void* policy; int32_t policy_per_env;   // linear (float) / tabular (uint8) rollout policy, NULL = uniform random
   const RowTable* rows;   // heterogeneous handles
 };
 

@@ -92,7 +92,7 @@ class NsgymHostOut(C.Structure):
 EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
     "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_unpack", "nsgym_step_host",
-    "nsgym_rollout", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_eval_w1", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
+    "nsgym_rollout", "nsgym_rollout_linear", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_eval_w1", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
     "nsgym_launch_count",
 ]
 
@@ -149,6 +149,8 @@ def load(build_if_missing: bool = False):
                                   C.c_int, C.c_void_p]
     lib.nsgym_fanout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
     lib.nsgym_snapshot_bytes.restype = C.c_size_t
+    lib.nsgym_rollout_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
+                                         C.c_int, C.c_void_p]
     lib.nsgym_snapshot_bytes.argtypes = [C.c_void_p]
     lib.nsgym_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
     lib.nsgym_restore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]

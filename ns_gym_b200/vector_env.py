@@ -353,16 +353,44 @@ class NSVectorEnv:
         return out
 
     # ---- fused K-step rollout ----
+    def policy_shape(self, per_env: bool = False):
+        """Shape of a device-side rollout policy: classic control ``[A, O + 1]`` float32 (row a: O
+        observation weights, then the bias; A = 1 for Box action spaces), gridworlds ``[n_cells]``
+        uint8 (action per cell); one leading ``num_envs`` axis when every env has its own."""
+        kind = self.program.env_kind
+        if kind in (nv.ENV_FROZENLAKE, nv.ENV_CLIFFWALKING, nv.ENV_BRIDGE):
+            shape = (int(self.program.spec.nrow) * int(self.program.spec.ncol),)
+        else:
+            n_obs = {nv.ENV_CARTPOLE: 4, nv.ENV_ACROBOT: 6, nv.ENV_MOUNTAINCAR: 2, nv.ENV_MOUNTAINCAR_CONT: 2,
+                     nv.ENV_PENDULUM: 3}[kind]
+            shape = (N_ACTIONS.get(kind, 1), n_obs + 1)
+        return ((self.num_envs,) + shape) if per_env else shape
+
     def rollout(self, k_steps: int, gamma: float = 1.0, returns: Optional[torch.Tensor] = None,
-                lengths: Optional[torch.Tensor] = None):
-        """K fused steps under the device-side uniform-random policy, state in registers."""
+                lengths: Optional[torch.Tensor] = None, policy: Optional[torch.Tensor] = None):
+        """K fused steps, state in registers, under a device-side policy: uniform-random actions, or
+        (``policy`` given, see ``policy_shape``) a linear policy on the observation -- ``argmax`` of
+        ``W obs + b`` for Discrete action spaces, the score itself for Box ones; a per-cell action
+        table for gridworlds.  A leading ``num_envs`` axis gives every env its own policy."""
         if returns is None:
             returns = torch.zeros(self.num_envs, dtype=torch.float32, device=self.device)
         if lengths is None:
             lengths = torch.zeros(self.num_envs, dtype=torch.int32, device=self.device)
         with torch.cuda.device(self.device):
-            nv.check(self.lib.nsgym_rollout(self._h, int(k_steps), 0, float(gamma), _ptr(returns), _ptr(lengths),
-                                            int(self.skip_updates), self._stream()), "nsgym_rollout")
+            if policy is None:
+                nv.check(self.lib.nsgym_rollout(self._h, int(k_steps), 0, float(gamma), _ptr(returns), _ptr(lengths),
+                                                int(self.skip_updates), self._stream()), "nsgym_rollout")
+            else:
+                shared, own = self.policy_shape(False), self.policy_shape(True)
+                if tuple(policy.shape) not in (shared, own):
+                    raise ValueError(f"policy shape {tuple(policy.shape)}: expected {shared} or {own}")
+                want = torch.uint8 if len(shared) == 1 else torch.float32
+                if policy.dtype != want or policy.device != self.device or not policy.is_contiguous():
+                    raise ValueError(f"policy must be a contiguous {want} tensor on {self.device}")
+                nv.check(self.lib.nsgym_rollout_linear(self._h, int(k_steps), _ptr(policy),
+                                                       int(tuple(policy.shape) == own and own != shared), float(gamma),
+                                                       _ptr(returns), _ptr(lengths), int(self.skip_updates),
+                                                       self._stream()), "nsgym_rollout_linear")
         return returns, lengths
 
     # ---- host-buffer (end-to-end) step through the C ABI ----

@@ -162,3 +162,83 @@ def test_planning_fanout_on_a_heterogeneous_batch():
     assert bool(torch.isfinite(ret).all()) and int(length.min()) >= 1
     # the copies keep evolving (in_sim_change): some parameter moved away from its root's value
     assert not torch.equal(plan.buffers["theta"], env.buffers["theta"].repeat_interleave(m, dim=1))
+
+
+def _linear_actions(w, obs, box):
+    """Host restatement of the device-side linear policy: float32 multiply-adds in index order."""
+    n, n_obs = obs.shape
+    wn = np.broadcast_to(w, (n,) + w.shape[-2:]).astype(np.float32)
+    v = wn[:, :, n_obs].copy()
+    for q in range(n_obs):
+        v = (v + (wn[:, :, q] * obs[:, None, q]).astype(np.float32)).astype(np.float32)
+    return v[:, 0] if box else np.argmax(v, axis=1).astype(np.int32)
+
+
+@pytest.mark.parametrize("name,precision,box,per_env", [
+    ("c1_cartpole_readme", "fp32", False, False), ("c1_cartpole_readme", "fp64", False, True),
+    ("c3_acrobot", "fp32", False, True), ("c3_mountaincar", "fp64", False, False),
+    ("c3_pendulum", "fp32", True, True), ("mountaincar_continuous", "fp64", True, False)])
+def test_linear_policy_rollout_equals_single_steps(name, precision, box, per_env):
+    """nsgym_rollout_linear: K fused steps under a device-side linear policy on the float32
+    observation = K launches with the actions a host restatement of that policy picks."""
+    import torch
+
+    case, n, K, seed = CASES[name], 2048, 33, 4321
+    a = _make(case, n, precision, seed)
+    b = _make(case, n, precision, seed)
+    r = np.random.default_rng([5, len(name), int(per_env)])
+    shape = a.policy_shape(per_env)
+    w = r.normal(0, 1, shape).astype(np.float32)
+    if box:
+        w *= np.float32(0.5)
+    wt = torch.as_tensor(w, device=a.device)
+    ret, length = a.rollout(K, gamma=1.0, policy=wt)
+    acc = torch.zeros(n, dtype=torch.float32, device=b.device)
+    for _ in range(K):
+        obs = b.observation().float().cpu().numpy()
+        act = _linear_actions(w, obs, box)
+        dtype = b.real if box else torch.int32
+        _, rew, _, _, _ = b.step(torch.as_tensor(act, device=b.device).to(dtype))
+        acc += rew
+    torch.cuda.synchronize()
+    for key in ("state", "theta", "t"):
+        assert torch.equal(a.buffers[key], b.buffers[key]), f"{name}: {key} differs after the linear-policy rollout"
+    assert torch.equal(ret, acc)
+
+
+@pytest.mark.parametrize("name,per_env", [("c5_bridge_uniform", False), ("c2_frozenlake8_drift", True),
+                                          ("cliff_terminal", False)])
+def test_tabular_policy_rollout_equals_single_steps(name, per_env):
+    """Gridworlds: the linear policy on the one-hot cell is an action table."""
+    import torch
+
+    case, n, K, seed = CASES[name], 2048, 41, 99
+    a = _make(case, n, "fp64", seed)
+    b = _make(case, n, "fp64", seed)
+    r = np.random.default_rng([6, len(name)])
+    table = r.integers(0, 4, a.policy_shape(per_env)).astype(np.uint8)
+    ret, length = a.rollout(K, gamma=1.0, policy=torch.as_tensor(table, device=a.device))
+    acc = torch.zeros(n, dtype=torch.float32, device=b.device)
+    rows = np.arange(n)
+    for _ in range(K):
+        cell = b.buffers["state"].reshape(-1).cpu().numpy()
+        act = (table[rows, cell] if per_env else table[cell]).astype(np.int32)
+        _, rew, _, _, _ = b.step(torch.as_tensor(act, device=b.device))
+        acc += rew
+    torch.cuda.synchronize()
+    for key in ("state", "theta", "t", "istate"):
+        x, y = a.buffers[key], b.buffers[key]
+        if x is not None:
+            assert torch.equal(x, y), f"{name}: {key} differs after the tabular-policy rollout"
+    assert torch.equal(ret, acc)
+
+
+def test_policy_argument_is_validated():
+    import torch
+
+    env = _make(CASES["c1_cartpole_readme"], 64, "fp32", 1)
+    assert env.policy_shape() == (2, 5) and env.policy_shape(True) == (64, 2, 5)
+    with pytest.raises(ValueError):
+        env.rollout(4, policy=torch.zeros(3, 5, device=env.device))
+    with pytest.raises(ValueError):
+        env.rollout(4, policy=torch.zeros(2, 5, device=env.device, dtype=torch.float64))
