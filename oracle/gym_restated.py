@@ -23,7 +23,6 @@ import importlib
 import math
 import sys
 import types
-from typing import Any
 
 import numpy as np
 

@@ -20,7 +20,6 @@ from __future__ import annotations
 import copy
 import math
 import warnings
-from typing import Any
 
 import numpy as np
 
