@@ -239,8 +239,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   // level 0 = fast class only, level 1 = + inline medium rules, level 2 = everything
   // (injected random tables -- parity tests -- also take level 2: the lean kernels fold the
   // "injected?" tests away)
-  // (a linear rollout policy is compiled into the general instantiation only)
-  int level = (P.n_slow > 0 || a.inj_u || a.inj_z || a.general_kernels || (op == OP_ROLLOUT && a.policy)) ? 2 : 0;
+  int level = (P.n_slow > 0 || a.inj_u || a.inj_z || a.general_kernels) ? 2 : 0;
   if (level == 0)
     for (int j = 0; j < NP; ++j)
       if (P.slot[j].flags & SF_MEDIUM) level = 1;
@@ -255,17 +254,28 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       } else classic_step_kernel<R, KIND, NP, 0><<<lean_grid, block, 0, stream>>>(P, io);
       break;
     case OP_RESET: classic_reset_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io); break;
-    case OP_ROLLOUT:
-      if (level == 2 || NP == 0)
-        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len,
-                                                                            static_cast<const float*>(a.policy), a.policy_per_env);
-      else if (level == 1) {
-        if constexpr (kHasMedium)
-          classic_rollout_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
-        else return cudaErrorInvalidValue;
-      } else
-        classic_rollout_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len);
+    case OP_ROLLOUT: {
+      const float* pol = static_cast<const float*>(a.policy);   // linear policy (nsgym_rollout_linear) or NULL
+      if (level == 2 || NP == 0) {
+        classic_rollout_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret,
+                                                                            a.len, pol, a.policy_per_env);
+      } else if (level == 1) {
+        if (pol)
+          classic_rollout_kernel<R, KIND, NP, 1, false, true><<<grid, block, 0, stream>>>(
+              P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len, pol, a.policy_per_env);
+        else
+          classic_rollout_kernel<R, KIND, NP, 1><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret,
+                                                                              a.len);
+      } else {
+        if (pol)
+          classic_rollout_kernel<R, KIND, NP, 0, false, true><<<grid, block, 0, stream>>>(
+              P, no_rows, io, a.k_steps, a.gamma, a.ret, a.len, pol, a.policy_per_env);
+        else
+          classic_rollout_kernel<R, KIND, NP, 0><<<grid, block, 0, stream>>>(P, no_rows, io, a.k_steps, a.gamma, a.ret,
+                                                                              a.len);
+      }
       break;
+    }
   }
   return cudaGetLastError();
 }
