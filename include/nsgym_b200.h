@@ -46,7 +46,7 @@
 extern "C" {
 #endif
 
-#define NSGYM_ABI_VERSION 1
+#define NSGYM_ABI_VERSION 2
 #define NSGYM_MAX_SLOTS 8
 #define NSGYM_MAX_THETA 8
 #define NSGYM_MAX_DIST 4
@@ -75,6 +75,8 @@ enum {
   NSGYM_FLAG_TERMINATED = 1,
   NSGYM_FLAG_TRUNCATED = 2,
   NSGYM_FLAG_RESET = 4,          /* this call performed the autoreset of the env */
+  NSGYM_FLAG_REJECTED = 8,       /* classic control: a fired update was rejected by the constraint checker and
+                                    theta kept its old value (ConstraintViolationWarning, classic_control.py:87-92) */
   NSGYM_FLAG_BAD_DIST = 128      /* gridworld: negative weight / sum != 1 (reference raises) */
 };
 
@@ -203,7 +205,7 @@ typedef struct {                 /* host-side results of nsgym_step_host; NULL m
 typedef struct NsgymHandle NsgymHandle;
 
 int nsgym_abi_version(void);
-size_t nsgym_sizeof(int which);  /* 0 NsgymSlot, 1 NsgymSpec, 2 NsgymLayout, 3 NsgymBuffers, 4 NsgymHostOut */
+size_t nsgym_sizeof(int which);  /* 0 NsgymSlot, 1 NsgymSpec, 2 NsgymLayout, 3 NsgymBuffers, 4 NsgymHostOut, 5 NsgymSnapshotInfo */
 const char* nsgym_last_error(void);
 
 /* replaces: wrapper construction (base.py:222-294, classic_control.py:27-58, toy_text.py:28-84,282-340,547-603) */
@@ -241,10 +243,34 @@ int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform
 int nsgym_unpack(NsgymHandle* h, uint8_t* d_terminated, uint8_t* d_truncated, uint8_t* d_was_reset,
                  int32_t* d_relative_time, uint8_t* d_env_change, void* stream);
 
+/* Episode bookkeeping for the batch in ONE launch over the outputs of the last step (what
+ * evaluate/run_experiment.py:91-148 does per env in Python: episode_reward += reward, count steps,
+ * stop at done / truncated), plus the counters a caller would otherwise need warnings for.
+ * d_running_return double[N] and d_running_length int32[N] are caller-owned running sums (zero them
+ * once); d_totals double[NSGYM_STAT_COUNT] accumulates over calls (zero it to start a report
+ * interval; sum it over ranks with one all-reduce):
+ *   STEPS env-steps taken (autoreset calls excluded), EPISODES finished, RETURN_SUM / LENGTH_SUM of
+ *   the finished episodes, TERMINATED, TRUNCATED, REJECTED steps on which the constraint checker
+ *   rejected a fired update (ConstraintViolationWarning, classic_control.py:87-92), BAD_DIST steps
+ *   on which the reference would have raised (NSGYM_FLAG_BAD_DIST). */
+enum { NSGYM_STAT_STEPS = 0, NSGYM_STAT_EPISODES, NSGYM_STAT_RETURN_SUM, NSGYM_STAT_LENGTH_SUM,
+       NSGYM_STAT_TERMINATED, NSGYM_STAT_TRUNCATED, NSGYM_STAT_REJECTED, NSGYM_STAT_BAD_DIST, NSGYM_STAT_COUNT };
+int nsgym_episode_stats(NsgymHandle* h, double* d_running_return, int32_t* d_running_length, double* d_totals,
+                        void* stream);
+
 /* Same call with HOST buffers: copies actions host->device, steps, copies the requested
- * results device->host, in `n_chunks` pipelined chunks, and returns after the last copy has
- * completed (synchronous).  This is the end-to-end call a host-side agent loop makes. */
-int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* out, int n_chunks);
+ * results device->host, in `n_chunks` pipelined chunks over the handle's own copy streams, and
+ * returns after the last copy has completed (synchronous).  This is the end-to-end call a
+ * host-side agent loop makes.  `stream` is the stream earlier calls on this handle were issued on
+ * (nsgym_reset, nsgym_step, nsgym_fanout ...): the pipeline is ordered after the work queued there.
+ * On an error nothing of the step is left in flight. */
+int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* out, int n_chunks, void* stream);
+
+/* Page-locked host memory for nsgym_step_host buffers (callers without torch): portable across
+ * devices; write_combined != 0 asks for write-combined memory (host writes / device reads only: the
+ * action buffer).  NULL on failure (nsgym_last_error). */
+void* nsgym_alloc_host(size_t bytes, int write_combined);
+void nsgym_free_host(void* p);
 
 /* K fused steps with state, theta and cursors in registers under a device-side policy
  * (MCTS-style random rollouts, benchmark_algorithms/MCTS.py:162-181).  policy 0 = uniform
@@ -281,12 +307,14 @@ int nsgym_rollout_linear(NsgymHandle* h, int k_steps, const void* d_policy, int 
 int nsgym_fanout(const NsgymHandle* src, NsgymHandle* dst, int fanout, int theta_from_init, void* stream);
 
 /* Device-side snapshot / restore of everything a step mutates (state, theta, t, cursors), packed
- * in that order into a caller buffer of nsgym_snapshot_bytes(); the Philox step counter travels
- * through *step_index.  restore(snapshot(x)) followed by the same calls reproduces the same
- * results bit for bit. */
+ * in that order into a caller buffer of nsgym_snapshot_bytes(); the host-side counters -- the Philox
+ * step counter and, for a planning copy, the TimeLimit steps counted since the copy -- travel
+ * through *info.  restore(snapshot(x)) followed by the same calls reproduces the same results bit
+ * for bit (rewinding a search: snapshot, rollout, restore, any number of times). */
+typedef struct { uint64_t step_index; int32_t plan_elapsed; int32_t _reserved; } NsgymSnapshotInfo;
 size_t nsgym_snapshot_bytes(const NsgymHandle* h);
-int nsgym_snapshot(NsgymHandle* h, void* d_dst, uint64_t* step_index, void* stream);
-int nsgym_restore(NsgymHandle* h, const void* d_src, uint64_t step_index, void* stream);
+int nsgym_snapshot(NsgymHandle* h, void* d_dst, NsgymSnapshotInfo* info, void* stream);
+int nsgym_restore(NsgymHandle* h, const void* d_src, const NsgymSnapshotInfo* info, void* stream);
 
 /* Time-indexed transition table of one gridworld env.
  * replaces: reading unwrapped.P (NSFrozenLakeWrapper._update_transition_prob_table toy_text.py:
@@ -319,6 +347,25 @@ int nsgym_eval_update(NsgymHandle* h, int slot, void* d_param, const int32_t* d_
 int nsgym_eval_w1(int dim, const double* d_u, const double* d_v, double* d_out, double* d_ref,
                   int64_t n, void* stream);
 
+/* Test entry: the NATIVE random draws of the handle's Philox streams (key = seed, counter = global env
+ * id, step index, block), made by the very device functions the step kernels call, for envs 0..n-1
+ * at Philox step `step_index` -- so the distributions of the draws the throughput kernels consume can
+ * be tested directly, and a host restatement (tests/philox_np.py) can be held to them value by value.
+ * d_out is double[planes][n] (float draws convert exactly).  Classic-control handles (in their
+ * precision): NORMAL the standard normal of parameter lane `lane` (update_functions/single_param.py:
+ * 79,111,149,345,446 draw rng.normal(mu, sigma) = mu + sigma z); RESET_UNIFORMS 4 planes, the
+ * initial-state uniforms.  Gridworld handles: DYN_UNIFORM the slip uniform (FrozenLake / Cliff
+ * categorical_sample, Bridge np.random.choice); DIRICHLET n_dist planes, RandomCategorical's
+ * Dirichlet(1,..,1) (distribution.py:37-38), `t` = redraw attempt.  Both: SCHED_UNIFORM the scheduler
+ * uniform of lane `lane` at episode time `t` (schedulers.py:28,177); GEOMETRIC MemorylessScheduler's
+ * inter-fire time Geometric(p) drawn from it (schedulers.py:112-113). */
+enum { NSGYM_DRAW_NORMAL = 0, NSGYM_DRAW_SCHED_UNIFORM = 1, NSGYM_DRAW_RESET_UNIFORMS = 2, NSGYM_DRAW_GEOMETRIC = 3,
+       NSGYM_DRAW_DYN_UNIFORM = 4, NSGYM_DRAW_DIRICHLET = 5,
+       NSGYM_DRAW_BOX_MULLER_SWEEP = 6 /* fp32 handles: the Box-Muller transform itself on chosen random bits --
+                                          radius bits step_index + i (sweep all 2^24), angle bits t */ };
+int nsgym_eval_draws(NsgymHandle* h, int what, int lane, int t, double p, uint64_t step_index, double* d_out,
+                     int64_t n, void* stream);
+
 /* Handle options.  NSGYM_OPT_GENERAL_KERNELS != 0: always launch the general kernel instantiations
  * (all rule classes, injection-capable) instead of the lean ones the library would pick for this
  * program -- same results (bit for bit in fp64 mode), used by the tests to tie the lean kernels to
@@ -331,6 +378,12 @@ void nsgym_set_seed(NsgymHandle* h, uint64_t seed);
 uint64_t nsgym_step_index(const NsgymHandle* h);        /* Philox counter (launches so far) */
 void nsgym_set_step_index(NsgymHandle* h, uint64_t v);
 int64_t nsgym_launch_count(const NsgymHandle* h);       /* kernels launched by this handle */
+/* Which kernel instantiation the handle's last step / rollout launched: the LEAN ones (what throughput
+ * runs use: native draws, fast [+ medium] rule classes only) or the GENERAL ones (every rule class,
+ * injection-capable -- what parity tests with injected tables run); -1 before the first step. */
+enum { NSGYM_KERNEL_LEAN_FAST = 0, NSGYM_KERNEL_LEAN_MEDIUM = 1, NSGYM_KERNEL_GENERAL = 2,
+       NSGYM_KERNEL_ROWS_LEAN = 3, NSGYM_KERNEL_ROWS_GENERAL = 4 };
+int nsgym_last_kernel_class(const NsgymHandle* h);
 
 #ifdef __cplusplus
 }

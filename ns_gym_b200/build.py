@@ -66,6 +66,30 @@ def _source_digest() -> str:
     return h.hexdigest()
 
 
+def _includes(path: str, seen: set) -> set:
+    """Files `path` includes with quotes, transitively (searched in csrc/ and include/)."""
+    import re
+
+    if path in seen or not os.path.isfile(path):
+        return seen
+    seen.add(path)
+    with open(path) as f:
+        for inc in re.findall(r'^\s*#\s*include\s*"([^"]+)"', f.read(), flags=re.M):
+            for d in (CSRC, INCLUDE):
+                _includes(os.path.join(d, inc), seen)
+    return seen
+
+
+def _unit_digest(name: str, extra, defines) -> str:
+    h = hashlib.sha256()
+    for path in sorted(_includes(os.path.join(CSRC, name), set())):
+        h.update(os.path.basename(path).encode())
+        with open(path, "rb") as f:
+            h.update(f.read())
+    h.update(repr((ARCH, [c for c in COMMON if c not in (INCLUDE, CSRC)], list(extra), list(defines))).encode())
+    return h.hexdigest()
+
+
 def is_current() -> bool:
     stamp = LIB_PATH + ".sha256"
     if not (os.path.exists(LIB_PATH) and os.path.exists(stamp)):
@@ -81,6 +105,19 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
     variant = bool(defines or out)
     if not force and not variant and is_current():
         return LIB_PATH
+    os.makedirs(LIB_DIR, exist_ok=True)
+    # one builder at a time (torchrun: every rank may find the library stale at once): the others
+    # wait on the lock and find it current when they get it
+    import fcntl
+
+    with open(os.path.join(LIB_DIR, ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        if not force and not variant and is_current():
+            return LIB_PATH
+        return _build_locked(verbose, ptxas_info, defines, out, variant)
+
+
+def _build_locked(verbose, ptxas_info, defines, out, variant) -> str:
     nvcc = _nvcc()
     lib_path = out or LIB_PATH
     obj_dir = OBJ_DIR if not variant else os.path.join(LIB_DIR, "obj_" + os.path.basename(lib_path))
@@ -89,6 +126,12 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
     def compile_unit(item):
         obj_name, (name, extra) = item
         obj = os.path.join(obj_dir, obj_name)
+        # an object is reused while the sources it includes (transitively) and its flags are unchanged
+        stamp, digest = obj + ".sha256", _unit_digest(name, extra, defines)
+        if not ptxas_info and os.path.exists(obj) and os.path.exists(stamp):
+            with open(stamp) as f:
+                if f.read().strip() == digest:
+                    return obj
         cmd = [nvcc, *ARCH, *COMMON, *extra, *[f"-D{d}" for d in defines], "-c", os.path.join(CSRC, name), "-o", obj]
         if ptxas_info:
             cmd[1:1] = ["-Xptxas", "-v"]
@@ -97,19 +140,26 @@ def build_library(force: bool = False, verbose: bool = False, ptxas_info: bool =
             raise RuntimeError(f"nvcc failed on {name}:\n{r.stdout}\n{r.stderr}")
         if verbose or ptxas_info:
             sys.stderr.write(r.stderr)
+        with open(stamp, "w") as f:
+            f.write(digest)
         return obj
 
     # longest units first; one nvcc per core
     order = sorted(UNITS.items(), key=lambda kv: (0 if "kind" in kv[0] else 1, kv[0]))
     with ThreadPoolExecutor(max_workers=max(2, os.cpu_count() or 4)) as pool:
         objs = list(pool.map(compile_unit, order))
-    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", lib_path, *objs]
+    # link next to the target and rename into place: a process that is dlopen'ing the old library
+    # keeps its (unlinked) file, nobody ever maps a half-written one
+    tmp_path = f"{lib_path}.tmp{os.getpid()}"
+    link = [nvcc, *ARCH, "-shared", "-Xcompiler", "-fPIC", "-o", tmp_path, *objs]
     r = subprocess.run(link, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")
+    os.replace(tmp_path, lib_path)
     if not variant:
-        with open(LIB_PATH + ".sha256", "w") as f:
+        with open(LIB_PATH + ".sha256.tmp", "w") as f:
             f.write(_source_digest())
+        os.replace(LIB_PATH + ".sha256.tmp", LIB_PATH + ".sha256")
     return lib_path
 
 

@@ -227,8 +227,16 @@ def _need_plane(slot, planes, j):
     """One integer state plane per parameter slot (list cursor or Memoryless next-fire time);
     ``planes`` maps slot position -> plane, allocated on first need."""
     if slot.istate_plane >= 0:
-        raise CompileError("a Memoryless scheduler cannot drive a StepWise / Cyclic update "
-                           "(one integer state plane per parameter)")
+        # MemorylessScheduler (schedulers.py:92-116) driving a list update (single_param.py:202-223,
+        # 388-408; distribution.py:100-130, 334-356): next-fire time (low 24 bits) and cursor (bits 24..30)
+        # share the slot's word (IstPack, nsgym_device.cuh)
+        if slot.ui[1] > 127:
+            raise CompileError("a Memoryless scheduler driving a StepWise / Cyclic update is limited to lists of "
+                               "127 entries (next-fire time and cursor share one integer state word)")
+        if not 0 <= slot.istate_init < (1 << 24):
+            raise CompileError("MemorylessScheduler: first transition time out of the packed range")
+        slot.ui[3] = 1
+        return
     slot.istate_plane = planes.setdefault(j, len(planes))
     slot.istate_init = 0
 
@@ -405,7 +413,7 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
                     autoreset: str = "next_step", seed: int = 0, env_id_offset: int = 0,
                     persistent_params: bool = False, max_episode_steps=None, base_params=None,
                     initial_prob_dist=None, modified_rewards=None, terminal_cliff: bool = False,
-                    map_name=None, desc=None, custom_horizon: int = 4096, _pools=None, _planes=None,
+                    map_name=None, desc=None, custom_horizon: int = 65536, _pools=None, _planes=None,
                     _finish=True, **_ignored) -> CompiledProgram:
     if env_id not in ENV_TABLE:
         raise CompileError(f"unknown environment id {env_id!r}; supported: {sorted(ENV_TABLE)}")
@@ -439,7 +447,17 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
     if is_grid:
         n_dist = 4 if kind == nv.ENV_CLIFFWALKING else 3
     spec.n_dist = n_dist
-    horizon = spec.max_episode_steps if spec.max_episode_steps > 0 else int(custom_horizon)
+    # A CustomScheduler is arbitrary Python: it is evaluated ONCE, ahead of time, for t = 0 .. horizon
+    # (same for every env and episode -- a stateful or random event_function cannot be lowered
+    # faithfully) into a fire bitmap.  The horizon covers every reachable t: an episode is at most
+    # `limit` steps and a planning copy taken at t <= limit steps on for at most another limit of
+    # its own (`_PLANNING_LIMIT`, <= 1000); without a TimeLimit (CliffWalking-v1, autoreset "none"
+    # stepping past the end) `custom_horizon` (default 65536) is the documented bound -- past it a
+    # CustomScheduler never fires.
+    if spec.max_episode_steps > 0 and autoreset == "next_step":
+        horizon = max(2 * spec.max_episode_steps, spec.max_episode_steps + 1000) + 2
+    else:
+        horizon = max(int(custom_horizon), 2 * spec.max_episode_steps + 1002)
 
     pools = _Pools() if _pools is None else _pools
     planes = {} if _planes is None else _planes

@@ -48,10 +48,12 @@ struct NsgymHandle {
   int64_t launches = 0;
   int n_istate = 0;
   cudaStream_t streams[kHostStreams]{};
+  cudaEvent_t host_event{};        // orders nsgym_step_host's side streams after the caller's stream
   bool streams_ready = false;
   nsg::RowTable rows;              // heterogeneous handles (nsgym_create_rows)
   int32_t plan_elapsed = -1;       // planning copy (nsgym_fanout): TimeLimit steps since the copy
   int32_t general_kernels = 0;     // NSGYM_OPT_GENERAL_KERNELS
+  int32_t kernel_class = -1;       // instantiation picked by the last step / rollout launch (NSGYM_KERNEL_*)
 
   bool grid() const { return nsg::is_grid_kind(spec.env_kind); }
   size_t real_bytes() const { return grid() ? 8 : (spec.precision == NSGYM_F64 ? 8 : 4); }
@@ -76,11 +78,16 @@ nsg::LaunchIO base_io(const NsgymHandle* h) {
   io.rows = h->rows.active ? &h->rows : nullptr;
   io.plan_elapsed = h->plan_elapsed;
   io.general_kernels = h->general_kernels;
+  io.sched_replay = h->spec.persistent_params ? 0 : 1;
   return io;
 }
 
-cudaError_t dispatch(NsgymHandle* h, nsg::LaunchOp op, const nsg::LaunchIO& io, cudaStream_t s) {
+cudaError_t dispatch(NsgymHandle* h, nsg::LaunchOp op, const nsg::LaunchIO& io_in, cudaStream_t s) {
   h->launches += 1;
+  nsg::LaunchIO io = io_in;
+  int32_t cls = -1;
+  io.kernel_class = &cls;
+  struct Keep { NsgymHandle* h; nsg::LaunchOp op; int32_t* c; ~Keep() { if (op != nsg::OP_RESET && *c >= 0) h->kernel_class = *c; } } keep{h, op, &cls};
   if (h->grid()) return nsg::launch_grid(op, h->spec, h->pools, io, s);
   if (h->spec.precision == NSGYM_F64) return nsg::launch_classic_f64(op, h->spec, h->pools, io, s);
   return nsg::launch_classic_f32(op, h->spec, h->pools, io, s);
@@ -244,6 +251,52 @@ unpack_kernel(const uint8_t* __restrict__ flags, const uint8_t* __restrict__ cha
 
 inline unsigned blocks_for(uint64_t n) { return unsigned((n + 255) / 256); }
 
+// Episode bookkeeping of a batch in one pass over the step's outputs (nsgym_episode_stats): running
+// return / length per env, finished episodes folded into the totals.  Persistent grid (a few CTAs
+// per SM, grid-stride): per-thread partial sums, warp shuffle + shared-memory reduction, one fp64
+// atomicAdd per total per CTA.
+constexpr int kStatTotals = NSGYM_STAT_COUNT;
+__global__ void __launch_bounds__(256)
+episode_stats_kernel(const float* __restrict__ reward, const uint8_t* __restrict__ flags, uint32_t n,
+                     double* __restrict__ run_ret, int32_t* __restrict__ run_len, double* __restrict__ totals) {
+  double acc[kStatTotals];
+#pragma unroll
+  for (int k = 0; k < kStatTotals; ++k) acc[k] = 0.0;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const uint32_t f = flags[i];
+    const bool stepped = !(f & NSGYM_FLAG_RESET);          // an autoreset call is not an env step
+    const bool ended = (f & (NSGYM_FLAG_TERMINATED | NSGYM_FLAG_TRUNCATED)) != 0;
+    double rr = run_ret[i] + (stepped ? double(reward[i]) : 0.0);
+    int32_t rl = run_len[i] + (stepped ? 1 : 0);
+    acc[NSGYM_STAT_STEPS] += stepped ? 1.0 : 0.0;
+    acc[NSGYM_STAT_EPISODES] += ended ? 1.0 : 0.0;
+    acc[NSGYM_STAT_RETURN_SUM] += ended ? rr : 0.0;
+    acc[NSGYM_STAT_LENGTH_SUM] += ended ? double(rl) : 0.0;
+    acc[NSGYM_STAT_TERMINATED] += (f & NSGYM_FLAG_TERMINATED) ? 1.0 : 0.0;
+    acc[NSGYM_STAT_TRUNCATED] += (f & NSGYM_FLAG_TRUNCATED) ? 1.0 : 0.0;
+    acc[NSGYM_STAT_REJECTED] += (f & NSGYM_FLAG_REJECTED) ? 1.0 : 0.0;
+    acc[NSGYM_STAT_BAD_DIST] += (f & NSGYM_FLAG_BAD_DIST) ? 1.0 : 0.0;
+    run_ret[i] = ended ? 0.0 : rr;
+    run_len[i] = ended ? 0 : rl;
+  }
+  __shared__ double part[8][kStatTotals];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < kStatTotals; ++k) {
+    double v = acc[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) part[warp][k] = v;
+  }
+  __syncthreads();
+  if (threadIdx.x < kStatTotals) {
+    double v = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) v += part[w][threadIdx.x];
+    if (v != 0.0) atomicAdd(totals + threadIdx.x, v);
+  }
+}
+
 }  // namespace
 
 namespace nsg {
@@ -265,6 +318,7 @@ size_t nsgym_sizeof(int which) {
     case 2: return sizeof(NsgymLayout);
     case 3: return sizeof(NsgymBuffers);
     case 4: return sizeof(NsgymHostOut);
+    case 5: return sizeof(NsgymSnapshotInfo);
     default: return 0;
   }
 }
@@ -317,8 +371,10 @@ void nsgym_destroy(NsgymHandle* h) {
   cudaFree(const_cast<double*>(h->pools.pool_f));
   cudaFree(const_cast<int32_t*>(h->pools.pool_i));
   cudaFree(const_cast<uint32_t*>(h->pools.bitmap));
-  if (h->streams_ready)
+  if (h->streams_ready) {
     for (auto& s : h->streams) cudaStreamDestroy(s);
+    cudaEventDestroy(h->host_event);
+  }
   delete h;
 }
 
@@ -410,14 +466,20 @@ int nsgym_unpack(NsgymHandle* h, uint8_t* d_terminated, uint8_t* d_truncated, ui
   return 0;
 }
 
-int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* out, int n_chunks) {
+int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* out, int n_chunks, void* stream) {
   if (!h || !h->bound) return fail(-1, "handle not bound");
   if (!h->initialised) return fail(-4, "step before reset");
   if (!h_action || !out) return fail(-1, "NULL argument");
   if (!h->streams_ready) {
     for (auto& s : h->streams) NSG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    NSG_CUDA(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
     h->streams_ready = true;
   }
+  // order the pipeline after whatever the caller's stream still has in flight on this handle's
+  // buffers (a reset, a device-side step, a planning copy): the side streams are non-blocking
+  // streams and would not wait for it by themselves
+  NSG_CUDA(cudaEventRecord(h->host_event, static_cast<cudaStream_t>(stream)));
+  for (auto& s : h->streams) NSG_CUDA(cudaStreamWaitEvent(s, h->host_event, 0));
   const int64_t n = h->spec.n_envs;
   if (n_chunks < 1) n_chunks = 1;
   if (n_chunks > n) n_chunks = int(n);
@@ -425,42 +487,62 @@ int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* ou
   int64_t per = ((n + n_chunks - 1) / n_chunks + 255) / 256 * 256;
   const size_t ab = h->action_bytes(), sb = h->state_bytes_per_env(), w = h->real_bytes();
   const int obs_words = kKinds[h->spec.env_kind].obs_words;
+  cudaError_t err = cudaSuccess;
+  const char* what = "";
+  auto copy = [&](void* dst, const void* src, size_t bytes, cudaMemcpyKind kind, cudaStream_t s, const char* name) {
+    if (err != cudaSuccess) return;
+    err = cudaMemcpyAsync(dst, src, bytes, kind, s);
+    if (err != cudaSuccess) what = name;
+  };
   int c = 0;
-  for (int64_t b = 0; b < n; b += per, ++c) {
+  for (int64_t b = 0; b < n && err == cudaSuccess; b += per, ++c) {
     const int64_t cnt = (n - b) < per ? (n - b) : per;
     cudaStream_t s = h->streams[c % kHostStreams];
-    NSG_CUDA(cudaMemcpyAsync(static_cast<char*>(h->buf.d_action) + size_t(b) * ab,
-                             static_cast<const char*>(h_action) + size_t(b) * ab, size_t(cnt) * ab,
-                             cudaMemcpyHostToDevice, s));
+    copy(static_cast<char*>(h->buf.d_action) + size_t(b) * ab, static_cast<const char*>(h_action) + size_t(b) * ab,
+         size_t(cnt) * ab, cudaMemcpyHostToDevice, s, "action H2D");
+    if (err != cudaSuccess) break;
     nsg::LaunchIO io = base_io(h);
     io.begin = b;
     io.count = cnt;
-    cudaError_t e = dispatch(h, nsg::OP_STEP, io, s);
-    if (e != cudaSuccess) return fail(-10, "step launch: %s", cudaGetErrorString(e));
-    if (out->h_reward)
-      NSG_CUDA(cudaMemcpyAsync(out->h_reward + b, h->buf.d_reward + b, size_t(cnt) * 4, cudaMemcpyDeviceToHost, s));
-    if (out->h_flags)
-      NSG_CUDA(cudaMemcpyAsync(out->h_flags + b, h->buf.d_flags + b, size_t(cnt), cudaMemcpyDeviceToHost, s));
-    if (out->h_change)
-      NSG_CUDA(cudaMemcpyAsync(out->h_change + b, h->buf.d_change + b, size_t(cnt), cudaMemcpyDeviceToHost, s));
+    err = dispatch(h, nsg::OP_STEP, io, s);
+    if (err != cudaSuccess) { what = "step launch"; break; }
+    if (out->h_reward) copy(out->h_reward + b, h->buf.d_reward + b, size_t(cnt) * 4, cudaMemcpyDeviceToHost, s, "reward D2H");
+    if (out->h_flags) copy(out->h_flags + b, h->buf.d_flags + b, size_t(cnt), cudaMemcpyDeviceToHost, s, "flags D2H");
+    if (out->h_change) copy(out->h_change + b, h->buf.d_change + b, size_t(cnt), cudaMemcpyDeviceToHost, s, "change D2H");
     if (out->h_state)
-      NSG_CUDA(cudaMemcpyAsync(static_cast<char*>(out->h_state) + size_t(b) * sb,
-                               static_cast<char*>(h->buf.d_state) + size_t(b) * sb, size_t(cnt) * sb,
-                               cudaMemcpyDeviceToHost, s));
+      copy(static_cast<char*>(out->h_state) + size_t(b) * sb, static_cast<char*>(h->buf.d_state) + size_t(b) * sb,
+           size_t(cnt) * sb, cudaMemcpyDeviceToHost, s, "state D2H");
     if (out->h_obs && h->buf.d_obs && obs_words)
-      NSG_CUDA(cudaMemcpyAsync(out->h_obs + b * obs_words, h->buf.d_obs + b * obs_words,
-                               size_t(cnt) * obs_words * 4, cudaMemcpyDeviceToHost, s));
+      copy(out->h_obs + b * obs_words, h->buf.d_obs + b * obs_words, size_t(cnt) * obs_words * 4,
+           cudaMemcpyDeviceToHost, s, "obs D2H");
     if (out->h_delta && h->buf.d_delta)
       for (int j = 0; j < h->spec.n_slots; ++j)
-        NSG_CUDA(cudaMemcpyAsync(static_cast<char*>(out->h_delta) + (size_t(j) * n + b) * w,
-                                 static_cast<char*>(h->buf.d_delta) + (size_t(j) * n + b) * w, size_t(cnt) * w,
-                                 cudaMemcpyDeviceToHost, s));
+        copy(static_cast<char*>(out->h_delta) + (size_t(j) * n + b) * w,
+             static_cast<char*>(h->buf.d_delta) + (size_t(j) * n + b) * w, size_t(cnt) * w, cudaMemcpyDeviceToHost, s,
+             "delta D2H");
   }
-  for (auto& s : h->streams) NSG_CUDA(cudaStreamSynchronize(s));
+  // synchronous call: nothing of this step is left in flight on the side streams, error or not
+  for (auto& s : h->streams) {
+    const cudaError_t e2 = cudaStreamSynchronize(s);
+    if (err == cudaSuccess && e2 != cudaSuccess) { err = e2; what = "stream synchronize"; }
+  }
+  if (err != cudaSuccess) return fail(-10, "nsgym_step_host: %s: %s", what, cudaGetErrorString(err));
   h->step_index += 1;
   if (h->plan_elapsed >= 0) h->plan_elapsed += 1;
   return 0;
 }
+
+void* nsgym_alloc_host(size_t bytes, int write_combined) {
+  void* p = nullptr;
+  const unsigned flags = cudaHostAllocPortable | (write_combined ? cudaHostAllocWriteCombined : 0u);
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, flags) != cudaSuccess) {
+    fail(-3, "cudaHostAlloc(%zu bytes) failed", bytes);
+    return nullptr;
+  }
+  return p;
+}
+
+void nsgym_free_host(void* p) { if (p) cudaFreeHost(p); }
 
 int nsgym_rollout(NsgymHandle* h, int k_steps, int policy, float gamma, float* d_return, int32_t* d_length,
                   int skip_updates, void* stream) {
@@ -575,6 +657,7 @@ int nsgym_transition_table(NsgymHandle* h, int64_t env, int n_times, double* d_p
   io.n = h->spec.n_envs; io.count = h->spec.n_envs;
   io.gid_offset = uint64_t(h->spec.env_id_offset); io.seed = h->spec.seed; io.step_index = h->step_index;
   io.rows = h->rows.active ? &h->rows : nullptr;
+  io.sched_replay = h->spec.persistent_params ? 0 : 1;
   io.plan_elapsed = -1;
   cudaError_t e = nsg::launch_table(h->spec, h->pools, io, env, n_times, d_prob, d_next, d_reward, d_done,
                                     static_cast<cudaStream_t>(stream));
@@ -610,18 +693,21 @@ int snapshot_copy(NsgymHandle* h, char* packed, bool to_packed, cudaStream_t s) 
 }
 }  // namespace
 
-int nsgym_snapshot(NsgymHandle* h, void* d_dst, uint64_t* step_index, void* stream) {
-  if (!h || !h->bound || !d_dst) return fail(-1, "NULL argument / handle not bound");
-  if (step_index) *step_index = h->step_index;
+int nsgym_snapshot(NsgymHandle* h, void* d_dst, NsgymSnapshotInfo* info, void* stream) {
+  if (!h || !h->bound || !d_dst || !info) return fail(-1, "NULL argument / handle not bound");
+  info->step_index = h->step_index;
+  info->plan_elapsed = h->plan_elapsed;
+  info->_reserved = 0;
   return snapshot_copy(h, static_cast<char*>(d_dst), true, static_cast<cudaStream_t>(stream));
 }
 
-int nsgym_restore(NsgymHandle* h, const void* d_src, uint64_t step_index, void* stream) {
-  if (!h || !h->bound || !d_src) return fail(-1, "NULL argument / handle not bound");
+int nsgym_restore(NsgymHandle* h, const void* d_src, const NsgymSnapshotInfo* info, void* stream) {
+  if (!h || !h->bound || !d_src || !info) return fail(-1, "NULL argument / handle not bound");
   if (int rc = snapshot_copy(h, const_cast<char*>(static_cast<const char*>(d_src)), false,
                              static_cast<cudaStream_t>(stream)))
     return rc;
-  h->step_index = step_index;
+  h->step_index = info->step_index;
+  h->plan_elapsed = info->plan_elapsed;     // the TimeLimit count of a planning copy rewinds with the state
   h->initialised = true;
   return 0;
 }
@@ -659,6 +745,49 @@ int nsgym_eval_w1(int dim, const double* d_u, const double* d_v, double* d_out, 
   return 0;
 }
 
+int nsgym_eval_draws(NsgymHandle* h, int what, int lane, int t, double p, uint64_t step_index, double* d_out,
+                     int64_t n, void* stream) {
+  if (!h || !d_out) return fail(-1, "NULL argument");
+  if (n <= 0 || n > (int64_t(1) << 28)) return fail(-1, "n out of range");
+  if (lane < 0 || lane >= NSGYM_MAX_SLOTS) return fail(-1, "lane out of range");
+  const bool grid = h->grid();
+  const bool ok = grid ? (what == NSGYM_DRAW_SCHED_UNIFORM || what == NSGYM_DRAW_GEOMETRIC ||
+                          what == NSGYM_DRAW_DYN_UNIFORM || what == NSGYM_DRAW_DIRICHLET)
+                       : ((what >= NSGYM_DRAW_NORMAL && what <= NSGYM_DRAW_GEOMETRIC) ||
+                          (what == NSGYM_DRAW_BOX_MULLER_SWEEP && h->spec.precision == NSGYM_F32));
+  if (!ok) return fail(-1, "draw kind %d does not exist for this env kind", what);
+  nsg::LaunchIO io{};
+  io.n = n; io.count = n;
+  io.gid_offset = uint64_t(h->spec.env_id_offset); io.seed = h->spec.seed; io.step_index = step_index;
+  io.sched_replay = h->spec.persistent_params ? 0 : 1;
+  io.plan_elapsed = -1;
+  if (what == NSGYM_DRAW_BOX_MULLER_SWEEP) io.begin = int64_t(step_index);   // first radius word of the sweep
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  cudaError_t e;
+  if (grid) e = nsg::launch_eval_draws_grid(io, h->spec.n_dist, what, lane, t, p, d_out, s);
+  else if (h->spec.precision == NSGYM_F64) e = nsg::launch_eval_draws_f64(io, what, lane, t, p, d_out, s);
+  else e = nsg::launch_eval_draws_f32(io, what, lane, t, p, d_out, s);
+  if (e != cudaSuccess) return fail(-10, "eval_draws launch: %s", cudaGetErrorString(e));
+  h->launches += 1;
+  return 0;
+}
+
+int nsgym_episode_stats(NsgymHandle* h, double* d_running_return, int32_t* d_running_length, double* d_totals,
+                        void* stream) {
+  if (!h || !h->bound) return fail(-1, "handle not bound");
+  if (!d_running_return || !d_running_length || !d_totals) return fail(-1, "NULL argument");
+  const uint32_t n = uint32_t(h->spec.n_envs);
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const unsigned want = blocks_for(n), cap = unsigned(sms) * 8u;
+  episode_stats_kernel<<<want < cap ? want : cap, 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      h->buf.d_reward, h->buf.d_flags, n, d_running_return, d_running_length, d_totals);
+  NSG_CUDA(cudaGetLastError());
+  h->launches += 1;
+  return 0;
+}
+
 int nsgym_set_option(NsgymHandle* h, int option, int64_t value) {
   if (!h) return fail(-1, "NULL handle");
   switch (option) {
@@ -671,5 +800,6 @@ void nsgym_set_seed(NsgymHandle* h, uint64_t seed) { if (h) h->spec.seed = seed;
 uint64_t nsgym_step_index(const NsgymHandle* h) { return h ? h->step_index : 0; }
 void nsgym_set_step_index(NsgymHandle* h, uint64_t v) { if (h) h->step_index = v; }
 int64_t nsgym_launch_count(const NsgymHandle* h) { return h ? h->launches : 0; }
+int nsgym_last_kernel_class(const NsgymHandle* h) { return h ? h->kernel_class : -1; }
 
 }  // extern "C"

@@ -197,6 +197,7 @@ static StepIO<R> build_io(const LaunchIO& a) {
   io.skip_updates = a.skip_updates; io.force_init = a.force_init;
   io.prefetch = (a.prefetch && !a.inj_u && !a.inj_z) ? 1 : 0;
   io.plan_elapsed = a.plan_elapsed;
+  io.sched_replay = a.sched_replay;
   uint32_t k0 = uint32_t(a.seed), k1 = uint32_t(a.seed >> 32);
   for (int r = 0; r < 10; ++r) {            // Philox4x32 key schedule (Weyl sequence)
     io.rk[r][0] = k0; io.rk[r][1] = k1;
@@ -219,10 +220,11 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     if constexpr (NP == 0) return cudaErrorInvalidValue;
     else {
       const HetT<R, NP> H = build_het<R, NP>(*a.rows);
+      const bool lean_rows = a.rows->lean && !a.general_kernels && !a.inj_u && !a.inj_z;
+      if (a.kernel_class) *a.kernel_class = lean_rows ? NSGYM_KERNEL_ROWS_LEAN : NSGYM_KERNEL_ROWS_GENERAL;
       switch (op) {
         case OP_STEP:
-          if (a.rows->lean && !a.general_kernels && !a.inj_u && !a.inj_z)
-            classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
+          if (lean_rows) classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
           else classic_step_het_kernel<R, KIND, NP, false><<<grid, block, 0, stream>>>(P, H, io);
           break;
         case OP_RESET: classic_reset_het_kernel<R, KIND, NP><<<grid, block, 0, stream>>>(P, H, io); break;
@@ -243,6 +245,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   if (level == 0)
     for (int j = 0; j < NP; ++j)
       if (P.slot[j].flags & SF_MEDIUM) level = 1;
+  if (a.kernel_class) *a.kernel_class = level == 2 ? NSGYM_KERNEL_GENERAL : (level == 1 ? NSGYM_KERNEL_LEAN_MEDIUM : NSGYM_KERNEL_LEAN_FAST);
   constexpr bool kHasMedium = true;
   const unsigned lean_grid = unsigned((a.count + block * NSGYM_LEAN_EPT - 1) / (block * NSGYM_LEAN_EPT));
   switch (op) {
@@ -344,6 +347,16 @@ static cudaError_t launch_eval_scalar_t(const NsgymSpec& spec, const DevicePools
   if (grid == 0) return cudaSuccess;
   eval_scalar_update_kernel<R><<<grid, block, 0, stream>>>(P, io, reinterpret_cast<R*>(param), time, istate, flag,
                                                            reinterpret_cast<R*>(delta));
+  return cudaGetLastError();
+}
+
+template <typename R>
+static cudaError_t launch_eval_draws_t(const LaunchIO& a, int what, int lane, int t, double p, double* out,
+                                       cudaStream_t stream) {
+  const StepIO<R> io = build_io<R>(a);
+  const unsigned grid = unsigned((a.count + 255) / 256);
+  if (grid == 0) return cudaSuccess;
+  eval_draws_kernel<R><<<grid, 256, 0, stream>>>(io, what, lane, t, p, out);
   return cudaGetLastError();
 }
 

@@ -13,4 +13,8 @@ cudaError_t launch_eval_scalar_f32(const NsgymSpec& spec, const DevicePools& poo
   return launch_eval_scalar_t<float>(spec, pools, slot, param, time, istate, flag, delta, inj_u, inj_z, n, seed,
                                      step_index, stream);
 }
+cudaError_t launch_eval_draws_f32(const LaunchIO& io, int what, int lane, int t, double p, double* out,
+                                  cudaStream_t stream) {
+  return launch_eval_draws_t<float>(io, what, lane, t, p, out, stream);
+}
 }  // namespace nsg

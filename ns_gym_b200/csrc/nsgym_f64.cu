@@ -15,4 +15,8 @@ cudaError_t launch_eval_scalar_f64(const NsgymSpec& spec, const DevicePools& poo
   return launch_eval_scalar_t<double>(spec, pools, slot, param, time, istate, flag, delta, inj_u, inj_z, n, seed,
                                       step_index, stream);
 }
+cudaError_t launch_eval_draws_f64(const LaunchIO& io, int what, int lane, int t, double p, double* out,
+                                  cudaStream_t stream) {
+  return launch_eval_draws_t<double>(io, what, lane, t, p, out, stream);
+}
 }  // namespace nsg

@@ -58,6 +58,10 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   const int block = 256;
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
+  if (a.kernel_class) {
+    if (het) *a.kernel_class = (a.rows->lean && !a.general_kernels && !a.inj_u) ? NSGYM_KERNEL_ROWS_LEAN : NSGYM_KERNEL_ROWS_GENERAL;
+    else *a.kernel_class = slow ? NSGYM_KERNEL_GENERAL : NSGYM_KERNEL_LEAN_FAST;
+  }
   if (het) {
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     switch (op) {
@@ -164,6 +168,16 @@ cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, in
     eval_dist_update_kernel<4><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
   else
     eval_dist_update_kernel<3><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_eval_draws_grid(const LaunchIO& a, int n_dist, int what, int lane, int t, double p, double* out,
+                                   cudaStream_t stream) {
+  const StepIO<double> io = build_io<double>(a);
+  const unsigned grid = unsigned((a.count + 255) / 256);
+  if (grid == 0) return cudaSuccess;
+  if (n_dist == 4) eval_grid_draws_kernel<4><<<grid, 256, 0, stream>>>(io, what, lane, t, p, out);
+  else eval_grid_draws_kernel<3><<<grid, 256, 0, stream>>>(io, what, lane, t, p, out);
   return cudaGetLastError();
 }
 

@@ -43,10 +43,12 @@ struct LaunchIO {
   uint64_t gid_offset, seed, step_index;
   int32_t skip_updates, force_init, prefetch, plan_elapsed;
   int32_t general_kernels;   // NSGYM_OPT_GENERAL_KERNELS
+  int32_t sched_replay;      // !persistent_params: stochastic schedulers replay their pattern every episode (base.py:383)
   // rollout
   int32_t k_steps; float gamma; float* ret; int32_t* len;
   const void* policy; int32_t policy_per_env;   // linear (float) / tabular (uint8) rollout policy, NULL = uniform random
   const RowTable* rows;   // heterogeneous handles
+  int32_t* kernel_class;  // out (host, may be NULL): which instantiation the launcher picked (NSGYM_KERNEL_*)
 };
 
 // each returns cudaError_t of the launch (cudaGetLastError)
@@ -68,6 +70,13 @@ cudaError_t launch_eval_scalar_f64(const NsgymSpec& spec, const DevicePools& poo
                                    const int32_t* time, int32_t* istate, uint8_t* flag, void* delta,
                                    const double* inj_u, const double* inj_z, int64_t n, uint64_t seed,
                                    uint64_t step_index, cudaStream_t stream);
+// native draws of the Philox streams (nsgym_eval_draws)
+cudaError_t launch_eval_draws_f32(const LaunchIO& io, int what, int lane, int t, double p, double* out,
+                                  cudaStream_t stream);
+cudaError_t launch_eval_draws_f64(const LaunchIO& io, int what, int lane, int t, double p, double* out,
+                                  cudaStream_t stream);
+cudaError_t launch_eval_draws_grid(const LaunchIO& io, int n_dist, int what, int lane, int t, double p, double* out,
+                                   cudaStream_t stream);
 cudaError_t launch_eval_w1(int dim, const double* u, const double* v, double* out, double* ref, int64_t n,
                            cudaStream_t stream);
 cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, int slot, double* param,

@@ -53,6 +53,11 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
                  (long long)e, j);
         return -1;
       }
+      if (a.ui[3] != key.ui[3]) {
+        snprintf(err, err_len, "row (env %lld, slot %d): a Memoryless scheduler driving a list update (packed cursor, "
+                 "ui[3]) must be declared by spec->slots[%d] for the whole batch", (long long)e, j, j);
+        return -1;
+      }
       if (int rc = validate_row_slot(&spec, &a, j, err, err_len)) return rc;
       lower_row<R>(spec, a, j, iw, rw, dw);
       {   // lean kernels: deterministic schedulers; fast / medium scalar rules or deterministic distribution rules

@@ -12,13 +12,8 @@ vector (NCCL over NVLink on GPUs, gloo in the CPU tests) -- latency-bound, off t
 from __future__ import annotations
 
 import os
-from dataclasses import dataclass
-
 import torch
 import torch.distributed as dist
-
-METRIC_KEYS = ("steps", "episodes", "return_sum", "length_sum", "terminated", "truncated")
-
 
 def shard_range(n_global: int, rank: int, world: int):
     """(first global env id, count) of rank's contiguous slice; remainders go to the low ranks."""
@@ -59,41 +54,46 @@ def max_over_ranks(value: float, device=None) -> float:
     return float(t.item())
 
 
-@dataclass
+def reduce_totals(totals: torch.Tensor) -> dict:
+    """Whole-job totals (sum over ranks of a ``native.STAT_KEYS`` vector) plus derived means."""
+    from .native import STAT_KEYS
+
+    tot = all_reduce_sum(totals.clone())
+    out = {k: float(v) for k, v in zip(STAT_KEYS, tot.tolist())}
+    ep = max(out["episodes"], 1.0)
+    out["mean_return"] = out["return_sum"] / ep
+    out["mean_length"] = out["length_sum"] / ep
+    return out
+
+
 class EpisodeStats:
-    """On-device episode accumulators, reduced over ranks on demand.
+    """On-device episode accumulators of one ``NSVectorEnv`` shard, reduced over ranks on demand.
 
-    ``update`` consumes the step kernel's outputs (reward float[N], flags uint8[N]); it keeps
-    running per-env return / length and folds finished episodes into six scalars."""
-    device: torch.device
-    n_envs: int
+    ``update()`` is ONE kernel launch (``nsgym_episode_stats``) over the step's reward / flag
+    outputs: per-env running return / length, finished episodes folded into eight fp64 totals
+    (``native.STAT_KEYS``; they include the constraint-rejection and bad-distribution counts, the
+    batch counterpart of the reference's ``ConstraintViolationWarning`` / ``ValueError``).  No host
+    synchronisation until ``reduce()`` reads the totals."""
 
-    def __post_init__(self):
-        self.running_return = torch.zeros(self.n_envs, dtype=torch.float64, device=self.device)
-        self.running_length = torch.zeros(self.n_envs, dtype=torch.int64, device=self.device)
-        self.totals = torch.zeros(len(METRIC_KEYS), dtype=torch.float64, device=self.device)
+    def __init__(self, env):
+        from . import native as nv
 
-    def update(self, reward: torch.Tensor, flags: torch.Tensor):
-        stepped = (flags & 4) == 0                      # NSGYM_FLAG_RESET calls are not env steps
-        term = (flags & 1) != 0
-        trunc = (flags & 2) != 0
-        ended = term | trunc
-        self.running_return += torch.where(stepped, reward.double(), torch.zeros_like(self.running_return))
-        self.running_length += stepped.long()
-        self.totals[0] += stepped.sum()
-        self.totals[1] += ended.sum()
-        self.totals[2] += self.running_return[ended].sum()
-        self.totals[3] += self.running_length[ended].sum()
-        self.totals[4] += term.sum()
-        self.totals[5] += trunc.sum()
-        self.running_return[ended] = 0
-        self.running_length[ended] = 0
+        self.env = env
+        self._nv = nv
+        dev, n = env.device, env.num_envs
+        self.running_return = torch.zeros(n, dtype=torch.float64, device=dev)
+        self.running_length = torch.zeros(n, dtype=torch.int32, device=dev)
+        self.totals = torch.zeros(len(nv.STAT_KEYS), dtype=torch.float64, device=dev)
+
+    def update(self):
+        """Fold the outputs of the env's last step into the accumulators."""
+        import ctypes as C
+
+        env, nv = self.env, self._nv
+        with torch.cuda.device(env.device):
+            nv.check(env.lib.nsgym_episode_stats(
+                env._h, C.c_void_p(self.running_return.data_ptr()), C.c_void_p(self.running_length.data_ptr()),
+                C.c_void_p(self.totals.data_ptr()), env._stream()), "nsgym_episode_stats")
 
     def reduce(self) -> dict:
-        """Whole-job totals (sum over ranks) plus derived means."""
-        tot = all_reduce_sum(self.totals.clone())
-        out = {k: float(v) for k, v in zip(METRIC_KEYS, tot.tolist())}
-        ep = max(out["episodes"], 1.0)
-        out["mean_return"] = out["return_sum"] / ep
-        out["mean_length"] = out["length_sum"] / ep
-        return out
+        return reduce_totals(self.totals)

@@ -14,13 +14,13 @@ from . import build as _build
 MAX_SLOTS = 8
 MAX_THETA = 8
 MAX_DIST = 4
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 ENV_CARTPOLE, ENV_ACROBOT, ENV_MOUNTAINCAR, ENV_MOUNTAINCAR_CONT, ENV_PENDULUM = 0, 1, 2, 3, 4
 ENV_FROZENLAKE, ENV_CLIFFWALKING, ENV_BRIDGE = 5, 6, 7
 F32, F64 = 0, 1
 AUTORESET_NONE, AUTORESET_NEXT_STEP = 0, 1
-FLAG_TERMINATED, FLAG_TRUNCATED, FLAG_RESET, FLAG_BAD_DIST = 1, 2, 4, 128
+FLAG_TERMINATED, FLAG_TRUNCATED, FLAG_RESET, FLAG_REJECTED, FLAG_BAD_DIST = 1, 2, 4, 8, 128
 
 SCHED_CONTINUOUS, SCHED_PERIODIC, SCHED_BITMAP, SCHED_BURST = 0, 1, 2, 3
 SCHED_WINDOW, SCHED_RANDOM, SCHED_DECAY, SCHED_MEMORYLESS = 4, 5, 6, 7
@@ -33,6 +33,11 @@ UPD_D_TARGET, UPD_D_LERP, UPD_D_STEPWISE, UPD_D_CYCLIC, UPD_D_RANDOM = 36, 37, 3
 CONS_NONE, CONS_REJECT_LE0, CONS_REJECT_LT0, CONS_ACRO_LENGTH1, CONS_ACRO_COM = 0, 1, 2, 3, 4
 
 OPT_GENERAL_KERNELS = 1
+STAT_KEYS = ("steps", "episodes", "return_sum", "length_sum", "terminated", "truncated", "rejected_updates",
+             "bad_dist")
+KERNEL_LEAN_FAST, KERNEL_LEAN_MEDIUM, KERNEL_GENERAL, KERNEL_ROWS_LEAN, KERNEL_ROWS_GENERAL = range(5)
+DRAW_NORMAL, DRAW_SCHED_UNIFORM, DRAW_RESET_UNIFORMS, DRAW_GEOMETRIC, DRAW_DYN_UNIFORM, DRAW_DIRICHLET, \
+    DRAW_BOX_MULLER_SWEEP = range(7)
 
 T_ENDED = 0x80000000
 T_TERMINATED_ONCE = 0x40000000
@@ -89,11 +94,15 @@ class NsgymHostOut(C.Structure):
                 ("h_reward", "h_flags", "h_change", "h_delta", "h_state", "h_obs")]
 
 
+class NsgymSnapshotInfo(C.Structure):
+    _fields_ = [("step_index", C.c_uint64), ("plan_elapsed", C.c_int32), ("_reserved", C.c_int32)]
+
+
 EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
-    "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_unpack", "nsgym_step_host",
-    "nsgym_rollout", "nsgym_rollout_linear", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_eval_w1", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
-    "nsgym_launch_count",
+    "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_unpack", "nsgym_episode_stats", "nsgym_step_host", "nsgym_alloc_host", "nsgym_free_host",
+    "nsgym_rollout", "nsgym_rollout_linear", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_eval_w1", "nsgym_eval_draws", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
+    "nsgym_launch_count", "nsgym_last_kernel_class",
 ]
 
 _lib = None
@@ -144,7 +153,12 @@ def load(build_if_missing: bool = False):
     lib.nsgym_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsgym_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
     lib.nsgym_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
-    lib.nsgym_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymHostOut), C.c_int]
+    lib.nsgym_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.nsgym_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymHostOut), C.c_int, C.c_void_p]
+    lib.nsgym_alloc_host.argtypes = [C.c_size_t, C.c_int]
+    lib.nsgym_alloc_host.restype = C.c_void_p
+    lib.nsgym_free_host.argtypes = [C.c_void_p]
+    lib.nsgym_free_host.restype = None
     lib.nsgym_rollout.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                   C.c_int, C.c_void_p]
     lib.nsgym_fanout.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]
@@ -152,8 +166,8 @@ def load(build_if_missing: bool = False):
     lib.nsgym_rollout_linear.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p, C.c_void_p,
                                          C.c_int, C.c_void_p]
     lib.nsgym_snapshot_bytes.argtypes = [C.c_void_p]
-    lib.nsgym_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(C.c_uint64), C.c_void_p]
-    lib.nsgym_restore.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64, C.c_void_p]
+    lib.nsgym_snapshot.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymSnapshotInfo), C.c_void_p]
+    lib.nsgym_restore.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymSnapshotInfo), C.c_void_p]
     lib.nsgym_transition_table.argtypes = [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                            C.c_void_p, C.c_void_p]
     lib.nsgym_set_option.argtypes = [C.c_void_p, C.c_int, C.c_int64]
@@ -162,6 +176,8 @@ def load(build_if_missing: bool = False):
     lib.nsgym_eval_update.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                       C.c_void_p]
+    lib.nsgym_eval_draws.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_uint64, C.c_void_p,
+                                     C.c_int64, C.c_void_p]
     lib.nsgym_set_seed.argtypes = [C.c_void_p, C.c_uint64]
     lib.nsgym_set_seed.restype = None
     lib.nsgym_step_index.restype = C.c_uint64
@@ -170,9 +186,10 @@ def load(build_if_missing: bool = False):
     lib.nsgym_set_step_index.restype = None
     lib.nsgym_launch_count.restype = C.c_int64
     lib.nsgym_launch_count.argtypes = [C.c_void_p]
+    lib.nsgym_last_kernel_class.argtypes = [C.c_void_p]
     if lib.nsgym_abi_version() != ABI_VERSION:
         raise NsgymError("libnsgym_b200.so ABI version differs from ns_gym_b200/native.py")
-    for which, st in enumerate((NsgymSlot, NsgymSpec, NsgymLayout, NsgymBuffers, NsgymHostOut)):
+    for which, st in enumerate((NsgymSlot, NsgymSpec, NsgymLayout, NsgymBuffers, NsgymHostOut, NsgymSnapshotInfo)):
         if lib.nsgym_sizeof(which) != C.sizeof(st):
             raise NsgymError(f"struct layout mismatch for {st.__name__}: C {lib.nsgym_sizeof(which)} "
                              f"vs ctypes {C.sizeof(st)}")

@@ -25,6 +25,18 @@ def _ptr(t: Optional[torch.Tensor]):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+def _mix64(*words: int) -> int:
+    """splitmix64-style hash of a few 64-bit words (planning-copy keys)."""
+    h = 0x9E3779B97F4A7C15
+    for w in words:
+        h = (h ^ (w & (2**64 - 1))) & (2**64 - 1)
+        h = (h * 0xBF58476D1CE4E5B9) & (2**64 - 1)
+        h ^= h >> 31
+        h = (h * 0x94D049BB133111EB) & (2**64 - 1)
+        h ^= h >> 29
+    return h
+
+
 class _LazyInfo(dict):
     """``info`` dict whose expensive entries (callables) are evaluated on first access."""
 
@@ -60,6 +72,8 @@ class NSVectorEnv:
                           seed=seed, device=device, want_obs=want_obs, want_delta=want_delta, rows=rows,
                           pools=pools, env_kwargs=dict(env_kwargs))
         self.env_order = None      # bucketed heterogeneous batches: storage position -> caller's env index
+        self.env_id_offset = int(env_id_offset)
+        self._n_copies = 0         # planning copies taken so far (mixed into their Philox key)
         self.lib = nv.load()
         self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
         self.num_envs = int(num_envs)
@@ -247,7 +261,12 @@ class NSVectorEnv:
         Philox streams (every env's stream is keyed by (seed, global env id))."""
         with torch.cuda.device(self.device):
             if seed is not None:
+                # reset(seed=s) is reproducible (base.py:386-388, 412-421 reseed every generator from
+                # s): new key, and the Philox step counter restarts, so the same seed replays the
+                # same draws whatever ran before
                 self.lib.nsgym_set_seed(self._h, int(seed) & (2**64 - 1))
+                if mask is None:
+                    self.lib.nsgym_set_step_index(self._h, 0)
             m = None
             if mask is not None:
                 m = mask.to(device=self.device, dtype=torch.uint8).contiguous()
@@ -290,6 +309,22 @@ class NSVectorEnv:
     def ground_truth_change(self) -> dict:
         c = self.buffers["change"]
         return {k: (c >> j) & 1 for j, k in enumerate(self.keys)}
+
+    def constraint_violations(self, warn: bool = False) -> int:
+        """Number of envs whose last step had a fired update REJECTED by the constraint checker
+        (theta kept its old value): the batch counterpart of the reference's per-env
+        ``ConstraintViolationWarning`` (classic_control.py:87-92).  Reads the flag bytes (one device
+        reduction + a host sync), so it is on demand; ``warn=True`` also issues the warning.
+        ``distributed.EpisodeStats`` accumulates the same count without a sync."""
+        n = int(((self.buffers["flags"] & nv.FLAG_REJECTED) != 0).sum().item())
+        if warn and n:
+            import warnings
+
+            from .wrappers import ConstraintViolationWarning
+            warnings.warn(f"{n} of {self.num_envs} envs rejected a parameter update that violates the "
+                          "environment's constraints; those parameters keep their previous value",
+                          ConstraintViolationWarning)
+        return n
 
     def ground_truth_delta(self) -> dict:
         d = self.buffers["delta"]
@@ -417,7 +452,7 @@ class NSVectorEnv:
             h_obs=h_out["obs"].data_ptr() if "obs" in h_out else 0)
         with torch.cuda.device(self.device):
             nv.check(self.lib.nsgym_step_host(self._h, C.c_void_p(h_actions.data_ptr()), C.byref(ho),
-                                              int(n_chunks)), "nsgym_step_host")
+                                              int(n_chunks), self._stream()), "nsgym_step_host")
 
     def host_bytes_per_step(self, h_actions: torch.Tensor, h_out: dict):
         h2d = h_actions.numel() * h_actions.element_size()
@@ -450,14 +485,19 @@ class NSVectorEnv:
         if rows is not None:                          # per-env rows (already in storage order): repeat them
             rows = np.repeat(self.rows, fanout, axis=0)
         if seed is None:
-            seed = (int(self.program.spec.seed) * 0x9E3779B97F4A7C15 + int(self.lib.nsgym_step_index(self._h)) + 1) \
-                & (2**64 - 1)
+            # _reseed_planning_env_rngs (base.py:433-441) gives every copy fresh generators: the key
+            # mixes the root's key, its Philox step counter AND the number of copies taken so far, so
+            # two copies of the same root step (MCTS.py:130: one deepcopy per simulation) draw
+            # different streams; `seed=` pins it for reproducible tests
+            self._n_copies += 1
+            seed = _mix64(int(self.program.spec.seed), int(self.lib.nsgym_step_index(self._h)), self._n_copies)
         plan = type(self).__new__(type(self))
         NSVectorEnv.__init__(
             plan, c["env_id"], tp, self.num_envs * fanout, change_notification=c["change_notification"],
             delta_change_notification=c["delta_change_notification"], in_sim_change=c["in_sim_change"],
             scalar_reward=c["scalar_reward"], persistent_params=c["persistent_params"], precision=c["precision"],
-            autoreset="none", seed=seed, env_id_offset=0, device=self.device, want_obs=c["want_obs"],
+            autoreset="none", seed=seed, env_id_offset=self.env_id_offset * fanout, device=self.device,
+            want_obs=c["want_obs"],
             want_delta=c["want_delta"], rows=rows, pools=c["pools"], **kw)
         theta_from_init = not (self.is_sim_env or self.delta_change_notification)
         with torch.cuda.device(self.device):
@@ -497,15 +537,15 @@ class NSVectorEnv:
     def snapshot(self):
         """Device copy of everything a step mutates; ``restore`` rewinds the batch to it."""
         buf = torch.empty(int(self.lib.nsgym_snapshot_bytes(self._h)), dtype=torch.uint8, device=self.device)
-        idx = C.c_uint64(0)
+        info = nv.NsgymSnapshotInfo()
         with torch.cuda.device(self.device):
-            nv.check(self.lib.nsgym_snapshot(self._h, _ptr(buf), C.byref(idx), self._stream()), "nsgym_snapshot")
-        return buf, int(idx.value)
+            nv.check(self.lib.nsgym_snapshot(self._h, _ptr(buf), C.byref(info), self._stream()), "nsgym_snapshot")
+        return buf, info
 
     def restore(self, snap):
-        buf, idx = snap
+        buf, info = snap
         with torch.cuda.device(self.device):
-            nv.check(self.lib.nsgym_restore(self._h, _ptr(buf), idx, self._stream()), "nsgym_restore")
+            nv.check(self.lib.nsgym_restore(self._h, _ptr(buf), C.byref(info), self._stream()), "nsgym_restore")
 
     # ---- notification control (base.py:443-458) ----
     def freeze(self, mode: bool = True):

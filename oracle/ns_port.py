@@ -189,7 +189,7 @@ def sched_fires(s: dict, st: SlotState, t, streams: EnvStreams | None, slot: int
 
     def uni():
         if streams is not None:
-            return streams.uniform(LANE_SCHED0 + slot)
+            return streams.sched_uniform(slot, t)
         return st.sched_rng.random()
 
     if k == "RandomScheduler":                      # schedulers.py:27-28
@@ -200,7 +200,7 @@ def sched_fires(s: dict, st: SlotState, t, streams: EnvStreams | None, slot: int
     if k == "MemorylessScheduler":                  # schedulers.py:110-116
         if t == st.transition_time:
             if streams is not None:
-                g = geometric_from_uniform(streams.uniform(LANE_SCHED0 + slot), s["p"])
+                g = geometric_from_uniform(streams.sched_uniform(slot, t), s["p"])
             else:
                 g = int(st.sched_rng.geometric(p=s["p"], size=(1,))[0])
             st.transition_time = g + t

@@ -90,6 +90,11 @@ class EnvStreams:
     def std_normal(self, slot: int) -> float:
         return float(self.z[self.clock.k, slot])
 
+    def sched_uniform(self, slot: int, t: int) -> float:
+        """Scheduler draw of parameter slot ``slot`` at episode time ``t``: positional here (the
+        table row of the current step); a native-stream stand-in may key it by ``t`` instead."""
+        return self.uniform(LANE_SCHED0 + slot)
+
     def dirichlet(self, slot: int, n: int):
         """The next Dirichlet(1,..,1) draw of parameter slot ``slot`` at the current step."""
         key = (self.clock.k, slot)
@@ -113,7 +118,7 @@ class SlotRng:
         return mu + sigma * self.s.std_normal(self.slot)
 
     def random(self):
-        return self.s.uniform(LANE_SCHED0 + self.slot)
+        return self.s.sched_uniform(self.slot, -1)
 
     def dirichlet(self, alpha):
         return np.array(self.s.dirichlet(self.slot, len(alpha)))

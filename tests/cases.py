@@ -281,6 +281,16 @@ CASES = {
             "gravity": U.IncrementUpdate(S.CustomScheduler(lambda t: t % 7 in (1, 2)), k=0.1),
         },
         wrapper=dict(change_notification=True), steps=60),
+    "cartpole_memoryless_lists": _c(
+        # MemorylessScheduler driving StepWise / Cyclic updates (schedulers.py:92-116 with
+        # single_param.py:202-223, 388-408): next-fire time and list cursor are both per-slot state
+        "CartPole-v1",
+        lambda S, U: {
+            "gravity": U.StepWiseUpdate(S.MemorylessScheduler(p=0.3, seed=3), [9.0, 10.5, 12.0, 8.5, 9.9]),
+            "length": U.CyclicUpdate(S.MemorylessScheduler(p=0.5, seed=4), [0.4, 0.5, 0.6, 0.55]),
+            "masspole": U.IncrementUpdate(S.MemorylessScheduler(p=0.2, seed=5), k=0.01),
+        },
+        wrapper=dict(change_notification=True, delta_change_notification=True), steps=90),
     # ---- Acrobot / MountainCar / Pendulum extras ----------------------------------------------
     "acrobot_constraints": _c(
         "Acrobot-v1",
@@ -344,6 +354,12 @@ CASES = {
         lambda S, U: {"P": U.DistributionNoUpdate(S.PeriodicScheduler(2))},
         wrapper=dict(initial_prob_dist=[0.6, 0.2, 0.2], change_notification=True,
                      delta_change_notification=True), steps=60),
+    "frozenlake4_memoryless_cyclic": _c(
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionCyclicUpdate(
+            S.MemorylessScheduler(p=0.4, seed=9), [[0.5, 0.25, 0.25], [0.8, 0.1, 0.1], [0.2, 0.4, 0.4]])},
+        wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
+                     delta_change_notification=True), steps=120),
     "bridge_stepwise": _c(
         "ns_gym/Bridge-v0",
         lambda S, U: {"P": U.DistributionStepWiseUpdate(

@@ -27,7 +27,14 @@ def oracle_trace(case, n_envs, seed, steps=None, actions=None):
     return tr, actions, u, z
 
 
-def gpu_env(case, n_envs, precision="fp64", autoreset="next_step"):
+def oracle_trace_streams(case, clock, per_env, actions):
+    """Trace of the oracle port driven by prepared per-env stream objects (tests/philox_np.py:
+    the kernels' native draws instead of numpy-drawn tables)."""
+    envs = harness.port_envs(case, len(per_env), per_env)
+    return vector.trace(vector.SyncVector(envs, per_env, clock), actions)
+
+
+def gpu_env(case, n_envs, precision="fp64", autoreset="next_step", **extra):
     """The case's batch on the CUDA path (heterogeneous cases: one tunable_params dict per env)."""
     import ns_gym_b200.schedulers as PS
     import ns_gym_b200.update_functions as PU
@@ -35,6 +42,7 @@ def gpu_env(case, n_envs, precision="fp64", autoreset="next_step"):
 
     kw = dict(precision=precision, autoreset=autoreset, want_delta=True, want_obs=True,
               **case.get("wrapper", {}), **case.get("make", {}))
+    kw.update(extra)
     if "params_of" in case:       # heterogeneous batch (nsgym_create_rows)
         return NSVectorEnv.heterogeneous(case["env_id"], [case["params_of"](PS, PU, e) for e in range(n_envs)], **kw)
     return NSVectorEnv(case["env_id"], case["params"](PS, PU), n_envs, **kw)
@@ -49,9 +57,12 @@ def gpu_run(env, actions, u, z, first_row=1, do_reset=True):
 
     n_envs = env.num_envs
     dev = env.device
-    U = torch.as_tensor(u, dtype=torch.float64, device=dev).contiguous()
-    Z = torch.as_tensor(z, dtype=torch.float64, device=dev).contiguous()
     K = len(actions)
+    if u is None:       # native Philox draws: nothing injected (the lean kernels where the program allows)
+        U = Z = [None] * (first_row + K)
+    else:
+        U = torch.as_tensor(u, dtype=torch.float64, device=dev).contiguous()
+        Z = torch.as_tensor(z, dtype=torch.float64, device=dev).contiguous()
     keys = env.keys
 
     def raw_state():
@@ -93,6 +104,7 @@ def gpu_run(env, actions, u, z, first_row=1, do_reset=True):
     for k2, v in lists.items():
         rec[k2] = np.stack(v)
     rec["_bad_dist"] = bad
+    rec["_kernel_class"] = int(env.lib.nsgym_last_kernel_class(env._h))
     return rec
 
 
@@ -171,8 +183,9 @@ def gpu_planning_trace(sc, n_envs, actions, u, z, precision="fp64"):
 def compare(ref, got, rtol=FP64_RTOL, atol=FP64_ATOL, float_obs_rtol=None, name=""):
     """Integer / flag arrays bit-exact; float arrays within (rtol, atol)."""
     for key in ref:
-        if key.startswith("_") or key not in got:
+        if key.startswith("_"):
             continue
+        assert key in got, f"{name}: the trace under test lacks '{key}'"
         a, b = np.asarray(ref[key]), np.asarray(got[key])
         assert a.shape == b.shape, f"{name}: {key} shape {a.shape} vs {b.shape}"
         if key in INT_KEYS or a.dtype.kind in "iub":

@@ -48,8 +48,19 @@ def test_scheduler_lowering():
                         4).spec.slots[0]
     assert (s.sched_op, s.start, s.end) == (nv.SCHED_CONTINUOUS, 5, 7)
     tp = {"gravity": U.IncrementUpdate(S.CustomScheduler(lambda t: t in (0, 499, 500)), k=1.0)}
-    p = compile_program("CartPole-v1", tp, 4)                        # horizon = TimeLimit 500
-    assert p.spec.slots[0].si[1] == 501
+    # the bitmap covers every reachable t: an episode (TimeLimit 500) plus a planning copy stepping on
+    # for another limit of its own (<= 1000): 2 * 500 + 500 + 2, one bit more for t = horizon
+    p = compile_program("CartPole-v1", tp, 4)
+    assert p.spec.slots[0].si[1] == 1503
+    # no TimeLimit to bound t (autoreset "none" may step past the end): the documented custom_horizon
+    p = compile_program("CartPole-v1", tp, 4, autoreset="none")
+    assert p.spec.slots[0].si[1] == 65537
+    # a Memoryless scheduler may drive a list update: next-fire time and cursor share the slot's word
+    tp = {"gravity": U.StepWiseUpdate(S.MemorylessScheduler(p=0.3, seed=3), [9.0, 10.0])}
+    s = compile_program("CartPole-v1", tp, 4).spec.slots[0]
+    assert (s.sched_op, s.upd_op, s.ui[3], s.istate_plane) == (nv.SCHED_MEMORYLESS, nv.UPD_STEPWISE, 1, 0)
+    with pytest.raises(CompileError):
+        compile_program("CartPole-v1", {"gravity": U.CyclicUpdate(S.MemorylessScheduler(p=0.3), list(range(200)))}, 4)
     tp = {"gravity": U.IncrementUpdate(S.MemorylessScheduler(p=0.3, seed=3), k=1.0)}
     s = compile_program("CartPole-v1", tp, 4).spec.slots[0]
     assert s.sched_op == nv.SCHED_MEMORYLESS and s.istate_plane == 0

@@ -30,20 +30,34 @@ def _free_port():
         return s.getsockname()[1]
 
 
+def _synthetic_totals(off, cnt):
+    """The totals vector (native.STAT_KEYS) a shard's device accumulator (nsgym_episode_stats) would
+    hold after 12 steps of deterministic synthetic outputs keyed by GLOBAL env id: reward 1 per
+    step, env g terminates every (g + 2) steps."""
+    from ns_gym_b200.native import STAT_KEYS
+
+    tot = torch.zeros(len(STAT_KEYS), dtype=torch.float64)
+    run = torch.zeros(cnt, dtype=torch.float64)
+    gids = torch.arange(off, off + cnt)
+    for k in range(1, 13):
+        ended = (k % (gids + 2)) == 0
+        run += 1.0
+        tot[0] += cnt
+        tot[1] += ended.sum()
+        tot[2] += run[ended].sum()
+        tot[3] += run[ended].sum()
+        tot[4] += ended.sum()
+        run[ended] = 0
+    return tot
+
+
 def _worker(rank, world, port, out):
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
                       WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
     r, _local, w = D.init_from_env(backend="gloo")
     assert (r, w) == (rank, world)
     off, cnt = D.shard_range(10, rank, world)
-    stats = D.EpisodeStats(torch.device("cpu"), cnt)
-    # deterministic synthetic step outputs keyed by GLOBAL env id: env g ends every (g + 2) steps
-    gids = torch.arange(off, off + cnt)
-    for k in range(1, 13):
-        reward = torch.ones(cnt)
-        flags = ((k % (gids + 2)) == 0).to(torch.uint8)            # terminated bit
-        stats.update(reward, flags)
-    red = stats.reduce()
+    red = D.reduce_totals(_synthetic_totals(off, cnt))
     slow = D.max_over_ranks(1.0 + rank)
     if rank == 0:
         out.put((red, slow))
@@ -63,11 +77,7 @@ def test_two_rank_metric_reduction_matches_single_process():
         assert p.exitcode == 0
     red, slow = q.get()
     # single-process truth over all 10 envs
-    stats = D.EpisodeStats(torch.device("cpu"), 10)
-    gids = torch.arange(10)
-    for k in range(1, 13):
-        stats.update(torch.ones(10), ((k % (gids + 2)) == 0).to(torch.uint8))
-    want = stats.reduce()
+    want = D.reduce_totals(_synthetic_totals(0, 10))
     assert red == want
     assert red["steps"] == 120 and red["episodes"] == sum(12 // (g + 2) for g in range(10))
     assert slow == 2.0
