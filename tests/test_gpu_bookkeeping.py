@@ -38,7 +38,7 @@ def test_host_step_is_ordered_after_the_callers_stream():
         torch.cuda.synchronize()
         for key in ("state", "theta", "t", "reward", "flags"):
             assert torch.equal(a_env.buffers[key], b_env.buffers[key]), (rep, key)
-        assert torch.equal(h_out["state"], a_env.buffers["state"].cpu())
+        assert torch.equal(h_out["obs"], a_env.buffers["obs"].cpu())
 
 
 @pytest.mark.parametrize("name", ["c1_cartpole_readme", "c5_bridge_uniform"])
@@ -180,4 +180,4 @@ def test_host_memory_helpers_and_error_paths():
     env.reset(seed=0)
     env.step_host(h_act, h_out, n_chunks=1000)         # more chunks than 256-env blocks: clamps
     torch.cuda.synchronize()
-    assert torch.equal(h_out["state"], env.buffers["state"].cpu())
+    assert torch.equal(h_out["obs"], env.buffers["obs"].cpu())

@@ -45,7 +45,7 @@ LEAN_FP64 = [("c1_cartpole_readme", "LEAN_FAST"), ("cartpole_silent", "LEAN_FAST
              ("c2_frozenlake8_stepchange", "LEAN_FAST"), ("c2_frozenlake8_drift", "LEAN_FAST"), ("cliff_drift", "LEAN_FAST"),
              ("c5_bridge_uniform", "LEAN_FAST"), ("c5_bridge_split", "LEAN_FAST"),
              ("frozenlake4_random_categorical", "GENERAL"), ("bridge_lipschitz_bounded", "GENERAL"),
-             ("c4_cartpole_rows", "ROWS_GENERAL"), ("het_cartpole_lean", "ROWS_LEAN"), ("c4_frozenlake8_rows", "ROWS_LEAN")]
+             ("c4_cartpole_rows", "ROWS_LEAN"), ("het_cartpole_lean", "ROWS_LEAN"), ("c4_frozenlake8_rows", "ROWS_LEAN")]
 
 
 @pytest.mark.parametrize("name,klass", LEAN_FP64)
@@ -88,7 +88,9 @@ def test_native_draw_kernels_track_the_oracle_fp32(name, klass):
     got_ended = (got["terminated"] | got["truncated"] | got["was_reset"])
     first_got = np.argmax(got_ended, axis=0)
     both = ended.any(0) & got_ended.any(0)
-    assert (np.abs(first_ref[both] - first_got[both]) <= 1).mean() > 0.95
+    assert np.array_equal(ended.any(0), got_ended.any(0)) or (ended.any(0) != got_ended.any(0)).mean() < 0.05
+    if both.any():
+        assert (np.abs(first_ref[both] - first_got[both]) <= 1).mean() > 0.95
 
 
 def test_stochastic_schedulers_replay_their_pattern_every_episode():
