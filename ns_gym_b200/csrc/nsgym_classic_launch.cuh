@@ -69,10 +69,6 @@ static SlotT<R> lower_slot(const NsgymSlot& a, int lane, int64_t t_max = (int64_
     case NSGYM_UPD_D_UNIFORM: b.flags |= SF_SLOW_UPD | SF_D_AFFINE; break;
     default: b.flags |= SF_SLOW_UPD; break;
   }
-  if (!(b.flags & SF_SLOW_SCHED)) {
-    if (b.start == 0 && b.span >= t_cap - 1) b.flags |= SF_NORANGE;      // t <= T_TIME_MASK always
-    if (b.mod_d == 0 && b.mod_on == INT32_MAX) b.flags |= SF_NOMOD;
-  }
   b.fa[0] = R(A); b.fa[1] = R(B); b.fa[2] = R(Ct);
   b.mu = R(a.uf[1]); b.sigma = R(a.uf[2]);
   // `v <= 0` -> v <= 0;  `v < 0` -> v <= -(smallest subnormal);  none -> v <= -inf (never)
@@ -256,14 +252,9 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     case OP_STEP:
       if (level == 2) classic_step_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io);
       else if (level == 1) {
-        if constexpr (kHasMedium) {
-          if (io.prefetch) classic_step_kernel<R, KIND, NP, 1, 1><<<lean_grid, block, 0, stream>>>(P, io);
-          else classic_step_kernel<R, KIND, NP, 1, 0><<<lean_grid, block, 0, stream>>>(P, io);
-        } else return cudaErrorInvalidValue;
-      } else {
-        if (io.prefetch) classic_step_kernel<R, KIND, NP, 0, 1><<<lean_grid, block, 0, stream>>>(P, io);
-        else classic_step_kernel<R, KIND, NP, 0, 0><<<lean_grid, block, 0, stream>>>(P, io);
-      }
+        if constexpr (kHasMedium) classic_step_kernel<R, KIND, NP, 1><<<lean_grid, block, 0, stream>>>(P, io);
+        else return cudaErrorInvalidValue;
+      } else classic_step_kernel<R, KIND, NP, 0><<<lean_grid, block, 0, stream>>>(P, io);
       break;
     case OP_RESET: classic_reset_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io); break;
     case OP_ROLLOUT: {
