@@ -172,13 +172,17 @@ typedef struct {
   const uint32_t* bitmap; int32_t n_bitmap_words;
   /* gridworld description (toy_text.py:426-469, :86-138; envs/Bridge.py:12,113-174) */
   int32_t nrow, ncol;
-  uint64_t hole_mask, goal_mask, start_mask; /* bit = cell index; nrow*ncol <= 64 */
+  uint64_t hole_mask, goal_mask, start_mask; /* bit = cell index; maps of <= 64 cells (else cell_class) */
   int32_t start_cell;
   int32_t split_mode;            /* Bridge: P_left / P_right by column of the current cell */
   float reward_f, reward_h, reward_g, reward_s; /* by destination cell letter */
   int32_t terminal_cliff;        /* CliffWalking */
-  int32_t _reserved;
+  int32_t n_cell_class;          /* 0, or nrow * ncol when cell_class is given */
+  const uint8_t* cell_class;     /* host, copied at create: letter of every cell (NSGYM_CELL_*), row-major; replaces
+                                    the three masks -- required for maps of more than 64 cells (toy_text.py:314-319
+                                    accepts any desc); nrow * ncol <= 256 */
 } NsgymSpec;
+enum { NSGYM_CELL_FROZEN = 0, NSGYM_CELL_HOLE = 1, NSGYM_CELL_GOAL = 2, NSGYM_CELL_START = 3 };
 
 typedef struct {                 /* bytes the caller must allocate for each bound buffer */
   size_t state, theta, t, istate, action, reward, flags, change, delta, obs;

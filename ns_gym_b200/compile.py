@@ -373,13 +373,18 @@ def _grid_masks(desc):
     rows = [r.decode() if isinstance(r, bytes) else "".join(
         c.decode() if isinstance(c, bytes) else c for c in r) for r in desc]
     nrow, ncol = len(rows), len(rows[0])
-    if nrow * ncol > 64:
-        raise CompileError("gridworld maps are limited to 64 cells")
+    if nrow * ncol > 256:
+        raise CompileError("gridworld maps are limited to 256 cells (one byte per cell in the kernels' map tables)")
     hole = goal = start = 0
-    starts = []
+    starts, letters = [], []
     for r, line in enumerate(rows):
+        if len(line) != ncol:
+            raise CompileError("gridworld map rows differ in length")
         for c, ch in enumerate(line):
             bit = 1 << (r * ncol + c)
+            letters.append({"F": nv.CELL_FROZEN, "H": nv.CELL_HOLE, "G": nv.CELL_GOAL, "S": nv.CELL_START}.get(ch))
+            if letters[-1] is None:
+                raise CompileError(f"unknown map letter {ch!r}")
             if ch == "H":
                 hole |= bit
             elif ch == "G":
@@ -387,7 +392,7 @@ def _grid_masks(desc):
             elif ch == "S":
                 start |= bit
                 starts.append(r * ncol + c)
-    return nrow, ncol, hole, goal, start, starts
+    return nrow, ncol, hole, goal, start, starts, letters
 
 
 def _lower_slot(slot, j, key, fn, kind, keys, order, pools, planes, horizon, n_dist):
@@ -495,7 +500,7 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
         if kind == nv.ENV_FROZENLAKE:
             if desc is None:
                 desc = FROZEN_LAKE_MAPS[map_name or ("8x8" if env_id == "FrozenLake8x8-v1" else "4x4")]
-            nrow, ncol, hole, goal, start, starts = _grid_masks(desc)
+            nrow, ncol, hole, goal, start, starts, letters = _grid_masks(desc)
             if len(starts) != 1:
                 raise CompileError("FrozenLake maps with several start cells are not supported")
             rw = {"F": 0.0, "H": 0.0, "G": 1.0, "S": 0.0}
@@ -503,19 +508,24 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
                 rw = {k: float(modified_rewards[k]) for k in "FHGS"}
             start_cell = starts[0]
         elif kind == nv.ENV_CLIFFWALKING:
-            nrow, ncol = 4, 12
+            nrow, ncol, letters = 4, 12, None
             hole = sum(1 << (3 * 12 + c) for c in range(1, 11))
             goal, start, start_cell = 1 << 47, 0, 36
             rw = {"H": -100.0, "G": 0.0, "F": -1.0, "S": -1.0}
             if modified_rewards:
                 rw.update({k: float(v) for k, v in modified_rewards.items()})
         else:
-            nrow, ncol, hole, goal, start, starts = _grid_masks(BRIDGE_MAP)
+            nrow, ncol, hole, goal, start, starts, letters = _grid_masks(BRIDGE_MAP)
             start_cell = 2 * ncol + 4                                            # envs/Bridge.py:110
             rw = {"F": 0.0, "H": -1.0, "G": 1.0, "S": 0.0}                       # envs/Bridge.py:159-174
             spec.split_mode = int(("P_left" in tunable_params) or ("P_right" in tunable_params))
         spec.nrow, spec.ncol = nrow, ncol
-        spec.hole_mask, spec.goal_mask, spec.start_mask = hole, goal, start
+        if nrow * ncol <= 64:
+            spec.hole_mask, spec.goal_mask, spec.start_mask = hole, goal, start
+        else:       # the masks hold 64 bits: larger maps (toy_text.py:314-319 accepts any desc) travel as letters
+            arr = (C.c_uint8 * len(letters))(*letters)
+            spec.cell_class, spec.n_cell_class = C.cast(arr, C.POINTER(C.c_uint8)), len(letters)
+            _map_keepalive = arr
         spec.start_cell = start_cell
         spec.reward_f, spec.reward_h, spec.reward_g, spec.reward_s = rw["F"], rw["H"], rw["G"], rw["S"]
         spec.terminal_cliff = int(bool(terminal_cliff))
@@ -523,6 +533,8 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
     prog = CompiledProgram(spec=spec, env_id=env_id, env_kind=kind, env_class=env_class, keys=keys,
                            precision=int(spec.precision), n_dist=n_dist)
     prog.horizon = horizon
+    if is_grid and spec.n_cell_class:
+        prog._map_keepalive = _map_keepalive      # the spec points into it until nsgym_create has copied it
     if _finish:
         _attach_pools(prog, pools)
     return prog

@@ -40,7 +40,7 @@ const KindInfo kKinds[NSGYM_ENV_COUNT] = {
 
 struct NsgymHandle {
   NsgymSpec spec;
-  nsg::DevicePools pools{nullptr, nullptr, nullptr};
+  nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr};
   NsgymBuffers buf{};
   bool bound = false;
   bool initialised = false;
@@ -144,11 +144,8 @@ int validate(const NsgymSpec* s) {
   if (grid) {
     const int want = s->env_kind == NSGYM_ENV_CLIFFWALKING ? 4 : 3;
     if (s->n_dist != want) return fail(-1, "n_dist %d, this env needs %d", s->n_dist, want);
-    if (s->nrow <= 0 || s->ncol <= 0 || s->nrow * s->ncol > 64)
-      return fail(-1, "gridworld maps are limited to 64 cells (got %dx%d)", s->nrow, s->ncol);
-    const int inv = (65536 + s->ncol - 1) / s->ncol;
-    for (int c = 0; c < s->nrow * s->ncol; ++c)
-      if (((c * inv) >> 16) != c / s->ncol) return fail(-1, "internal: reciprocal division inexact");
+    if (s->nrow <= 0 || s->ncol <= 0 || s->nrow * s->ncol > 256)
+      return fail(-1, "gridworld maps are limited to 256 cells (got %dx%d)", s->nrow, s->ncol);
     if (s->start_cell < 0 || s->start_cell >= s->nrow * s->ncol) return fail(-1, "start_cell out of range");
     if (s->env_kind != NSGYM_ENV_BRIDGE && s->n_slots != 1) return fail(-1, "this env has exactly one parameter, P");
   } else if (s->precision != NSGYM_F32 && s->precision != NSGYM_F64) {
@@ -343,8 +340,14 @@ int nsgym_create(const NsgymSpec* spec, NsgymHandle** out) {
   int rc = upload(spec->pool_f, spec->n_pool_f, &h->pools.pool_f);
   if (!rc) rc = upload(spec->pool_i, spec->n_pool_i, &h->pools.pool_i);
   if (!rc) rc = upload(spec->bitmap, spec->n_bitmap_words, &h->pools.bitmap);
+  if (!rc && h->grid()) {
+    uint32_t words[328];
+    char err[256] = "";
+    const int n_words = nsg::build_grid_tables(*spec, words, err, sizeof err);
+    rc = n_words < 0 ? fail(-1, "%s", err) : upload(words, n_words, &h->pools.grid_tab);
+  }
   if (rc) { nsgym_destroy(h); return rc; }
-  h->spec.pool_f = nullptr; h->spec.pool_i = nullptr; h->spec.bitmap = nullptr;
+  h->spec.pool_f = nullptr; h->spec.pool_i = nullptr; h->spec.bitmap = nullptr; h->spec.cell_class = nullptr;
   *out = h;
   return 0;
 }
@@ -371,6 +374,7 @@ void nsgym_destroy(NsgymHandle* h) {
   cudaFree(const_cast<double*>(h->pools.pool_f));
   cudaFree(const_cast<int32_t*>(h->pools.pool_i));
   cudaFree(const_cast<uint32_t*>(h->pools.bitmap));
+  cudaFree(const_cast<uint32_t*>(h->pools.grid_tab));
   if (h->streams_ready) {
     for (auto& s : h->streams) cudaStreamDestroy(s);
     cudaEventDestroy(h->host_event);

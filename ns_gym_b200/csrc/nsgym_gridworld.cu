@@ -1,5 +1,8 @@
 // Gridworld kernels (FrozenLake / CliffWalking / Bridge).  Probabilities are always fp64 and
 // this unit is built with -fmad=false: cumulative sums and W1 distances match NumPy exactly.
+#include <cstdio>
+#include <cstring>
+
 #include "nsgym_grid.cuh"
 #include "nsgym_classic_launch.cuh"
 
@@ -11,9 +14,9 @@ static GridProgram<MAXP> build_grid_program(const NsgymSpec& spec, const DeviceP
   G.base = build_program_by_index<MAXP>(spec, pools);   // slot index == theta index
   for (int i = 0; i < 3; ++i)
     for (int k = 0; k < NSGYM_MAX_DIST; ++k) G.dist_init[i][k] = spec.theta_init[i][k];
-  G.hole_mask = spec.hole_mask; G.goal_mask = spec.goal_mask; G.start_mask = spec.start_mask;
+  G.tab = pools.grid_tab;
   G.nrow = spec.nrow; G.ncol = spec.ncol;
-  G.inv_ncol = (65536 + spec.ncol - 1) / spec.ncol;
+  G.n_cells = spec.nrow * spec.ncol;
   G.start_cell = spec.start_cell;
   G.n_dist = spec.n_dist; G.split_mode = spec.split_mode; G.terminal_cliff = spec.terminal_cliff;
   G.reward_f = spec.reward_f; G.reward_h = spec.reward_h; G.reward_g = spec.reward_g; G.reward_s = spec.reward_s;
@@ -169,6 +172,51 @@ cudaError_t launch_eval_dist(const NsgymSpec& spec, const DevicePools& pools, in
   else
     eval_dist_update_kernel<3><<<grid, block, 0, stream>>>(G, io, param, time, istate, flag, delta);
   return cudaGetLastError();
+}
+
+int build_grid_tables(const NsgymSpec& spec, uint32_t* words, char* err, size_t err_len) {
+  const int nrow = spec.nrow, ncol = spec.ncol, n = nrow * ncol;
+  if (nrow <= 0 || ncol <= 0 || n > GRID_MAX_CELLS) {
+    snprintf(err, err_len, "gridworld maps are limited to %d cells (got %dx%d)", GRID_MAX_CELLS, nrow, ncol);
+    return -1;
+  }
+  if (spec.cell_class ? spec.n_cell_class != n : n > 64) {
+    snprintf(err, err_len, spec.cell_class ? "n_cell_class must equal nrow * ncol"
+                                           : "maps of more than 64 cells need cell_class (the masks hold 64 bits)");
+    return -1;
+  }
+  uint8_t bytes[GRID_TAB_WORDS * 4] = {};
+  const bool cliff = spec.env_kind == NSGYM_ENV_CLIFFWALKING;
+  for (int c = 0; c < n; ++c) {
+    const int row = c / ncol, col = c % ncol;
+    for (int b = 0; b < 4; ++b) {
+      // CliffWalking: UP RIGHT DOWN LEFT (toy_text.py:74-76); FrozenLake / Bridge: LEFT DOWN RIGHT UP
+      // (toy_text.py:321-324, envs/Bridge.py:14-17); the clamp is "out of bounds -> stay" for unit moves
+      const int dr = cliff ? (b == 2) - (b == 0) : (b == 1) - (b == 3);
+      const int dc = cliff ? (b == 1) - (b == 3) : (b == 2) - (b == 0);
+      const int r2 = row + dr < 0 ? 0 : (row + dr > nrow - 1 ? nrow - 1 : row + dr);
+      const int c2 = col + dc < 0 ? 0 : (col + dc > ncol - 1 ? ncol - 1 : col + dc);
+      bytes[c * 4 + b] = uint8_t(r2 * ncol + c2);
+    }
+    uint32_t cls = 0;
+    if (spec.cell_class) {
+      const uint8_t letter = spec.cell_class[c];
+      if (letter > NSGYM_CELL_START) { snprintf(err, err_len, "cell_class[%d] = %d is not a NSGYM_CELL_* letter", c, letter); return -1; }
+      cls = letter == NSGYM_CELL_HOLE ? CELL_HOLE : letter == NSGYM_CELL_GOAL ? CELL_GOAL : letter == NSGYM_CELL_START ? CELL_START : 0;
+    } else {
+      const uint64_t bit = 1ull << c;
+      cls = ((spec.hole_mask & bit) ? CELL_HOLE : 0) | ((spec.goal_mask & bit) ? CELL_GOAL : 0) |
+            ((spec.start_mask & bit) ? CELL_START : 0);
+    }
+    if (col < (ncol >> 1)) cls |= CELL_LEFT;                     // envs/Bridge.py:148-157
+    bytes[4 * n + c] = uint8_t(cls);
+  }
+  std::memcpy(words, bytes, sizeof bytes);
+  for (uint32_t c = 0; c < 8; ++c) {        // reward of the destination letter: hole > goal > start > frozen
+    const float r = (c & CELL_HOLE) ? spec.reward_h : (c & CELL_GOAL) ? spec.reward_g : (c & CELL_START) ? spec.reward_s : spec.reward_f;
+    std::memcpy(words + GRID_TAB_WORDS + c, &r, 4);
+  }
+  return GRID_TAB_TOTAL_WORDS;
 }
 
 cudaError_t launch_eval_draws_grid(const LaunchIO& a, int n_dist, int what, int lane, int t, double p, double* out,

@@ -13,7 +13,12 @@ struct DevicePools {
   const double* pool_f;
   const int32_t* pool_i;
   const uint32_t* bitmap;
+  const uint32_t* grid_tab;   // gridworld map tables (nsgym_grid.cuh: next[4 n] ++ cls[n]), NULL for classic control
 };
+
+// Map tables of a gridworld spec, as the kernels read them (host side; nsgym_create uploads them).
+// Returns the number of 32-bit words written to `words` (capacity 328), or -1 with `err` set.
+int build_grid_tables(const NsgymSpec& spec, uint32_t* words, char* err, size_t err_len);
 
 // Per-env rows of a heterogeneous handle (nsgym_create_rows): lowered, only the words that vary
 // between envs kept, as SoA planes in device memory owned by the handle.

@@ -33,6 +33,7 @@ UPD_D_TARGET, UPD_D_LERP, UPD_D_STEPWISE, UPD_D_CYCLIC, UPD_D_RANDOM = 36, 37, 3
 CONS_NONE, CONS_REJECT_LE0, CONS_REJECT_LT0, CONS_ACRO_LENGTH1, CONS_ACRO_COM = 0, 1, 2, 3, 4
 
 OPT_GENERAL_KERNELS = 1
+CELL_FROZEN, CELL_HOLE, CELL_GOAL, CELL_START = 0, 1, 2, 3
 STAT_KEYS = ("steps", "episodes", "return_sum", "length_sum", "terminated", "truncated", "rejected_updates",
              "bad_dist")
 KERNEL_LEAN_FAST, KERNEL_LEAN_MEDIUM, KERNEL_GENERAL, KERNEL_ROWS_LEAN, KERNEL_ROWS_GENERAL = range(5)
@@ -72,7 +73,8 @@ class NsgymSpec(C.Structure):
         ("hole_mask", C.c_uint64), ("goal_mask", C.c_uint64), ("start_mask", C.c_uint64),
         ("start_cell", C.c_int32), ("split_mode", C.c_int32),
         ("reward_f", C.c_float), ("reward_h", C.c_float), ("reward_g", C.c_float),
-        ("reward_s", C.c_float), ("terminal_cliff", C.c_int32), ("_reserved", C.c_int32),
+        ("reward_s", C.c_float), ("terminal_cliff", C.c_int32), ("n_cell_class", C.c_int32),
+        ("cell_class", C.POINTER(C.c_uint8)),
     ]
 
 

@@ -360,6 +360,14 @@ CASES = {
             S.MemorylessScheduler(p=0.4, seed=9), [[0.5, 0.25, 0.25], [0.8, 0.1, 0.1], [0.2, 0.4, 0.4]])},
         wrapper=dict(initial_prob_dist=[1, 0, 0], change_notification=True,
                      delta_change_notification=True), steps=120),
+    "frozenlake12_custom_map": _c(
+        # a 12x12 desc (144 cells): the wrapper accepts any map (toy_text.py:314-319)
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionDecrementUpdate(S.PeriodicScheduler(2), k=0.04)},
+        wrapper=dict(initial_prob_dist=[0.8, 0.1, 0.1], change_notification=True, delta_change_notification=True),
+        make=dict(desc=["SFFFFFFFFFFF", "FFFHFFFFFHFF", "FFFFFFFFFFFF", "FHFFFFHFFFFF", "FFFFFFFFFFHF", "FFFFHFFFFFFF",
+                        "FFFFFFFFFFFF", "FFHFFFFFHFFF", "FFFFFFFFFFFF", "FFFFFHFFFFFF", "FHFFFFFFFHFF", "FFFFFFFFFFFG"],
+                  max_episode_steps=60), steps=150),
     "bridge_stepwise": _c(
         "ns_gym/Bridge-v0",
         lambda S, U: {"P": U.DistributionStepWiseUpdate(
