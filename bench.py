@@ -382,13 +382,23 @@ def time_steps(shards, actions, steps, warmup, dist=None, rollout_k=0, policy=No
         def launch():
             env.rollout(rollout_k, 1.0, ret, length, policy=pol)
     else:
-        def launch():
-            for s, a in zip(shards, actions):
-                s.step_raw(a)
+        if len(shards) > 1:           # C4: the shards of a mixed batch are stepped by one host call
+            from ns_gym_b200.vector_env import MixedVectorEnv
+
+            mixed = MixedVectorEnv(shards)
+
+            def launch():
+                mixed.step_raw(actions)
+        else:
+            def launch():
+                shards[0].step_raw(actions[0])
     return _time_launches(launch, steps, warmup, dist)
 
 
-def _time_launches(launch, steps, warmup, dist=None):
+def _time_launches(launch, steps, warmup, dist=None, segments=5):
+    """W untimed + EXACTLY `steps` timed launches between two CUDA events on the launching stream
+    (barrier + synchronize on both sides).  Intermediate events split the run into `segments`
+    repetitions (median of 5); returns (total seconds, [seconds per launch of every segment])."""
     import torch
 
     for _ in range(warmup):
@@ -397,15 +407,122 @@ def _time_launches(launch, steps, warmup, dist=None):
     if dist is not None:
         dist.barrier()
         torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for _ in range(steps):
+    segments = max(1, min(segments, steps))
+    cuts = [round(k * steps / segments) for k in range(segments + 1)]
+    ev = [torch.cuda.Event(enable_timing=True) for _ in cuts]
+    ev[0].record()
+    nxt = 1
+    for k in range(steps):
         launch()
-    e1.record()
+        if k + 1 == cuts[nxt]:
+            ev[nxt].record()
+            nxt += 1
     torch.cuda.synchronize()
     if dist is not None:
         dist.barrier()
-    return e0.elapsed_time(e1) * 1e-3
+    per_launch = [ev[k].elapsed_time(ev[k + 1]) * 1e-3 / (cuts[k + 1] - cuts[k]) for k in range(segments)]
+    return ev[0].elapsed_time(ev[-1]) * 1e-3, per_launch
+
+
+def load_peak():
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            return float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def load_traffic():
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            return json.load(f)
+    return {}
+
+
+# BASELINE.json configs next to the headline workload: timed briefly in every default run so that the
+# driver's bench line carries them (roofline.workloads)
+TABLE_WORKLOADS = ["c1_cartpole_fp64", "c2_frozenlake8_16m", "c3_acrobot", "c3_acrobot_fp64", "c3_mountaincar",
+                   "c3_mountaincar_fp64", "c3_pendulum", "c3_pendulum_fp64", "c4_hetero", "c5_bridge",
+                   "c5_bridge_rollout32", "c1_cartpole_rollout32"]
+
+
+def quick_measure(workload, rank=0, seed=0, launches=30, warmup=5):
+    """{steps_per_s, us_per_launch, frac_algorithmic, frac_physical, ...} of one workload on this GPU:
+    `launches` timed launches (CUDA events) at the workload's own batch size."""
+    import torch
+
+    wl = WORKLOADS[workload]
+    n_envs = 1 << wl["log2_envs"]
+    env, _case = build_env(workload, n_envs, rank, seed=seed)
+    shards = list(getattr(env, "shards", [env]))
+    env.reset(seed=seed)
+    actions = [random_actions(s, 1234 + rank + 17 * k) for k, s in enumerate(shards)]
+    rollout_k = int(wl.get("rollout_k", 0))
+    secs, per = time_steps(shards, actions, launches, warmup, None, rollout_k, "random")
+    med = sorted(per)[len(per) // 2]
+    peak, _ = load_peak()
+    traffic = load_traffic().get(workload)
+    out = {"steps_per_s": n_envs * max(rollout_k, 1) / med, "us_per_launch": med * 1e6 / len(shards),
+           "envs": n_envs, "launches_per_step": len(shards)}
+    if not rollout_k:
+        out["frac_algorithmic"] = env.bytes_per_step * n_envs / med / 1e9 / peak
+        out["frac_physical"] = (traffic / med / 1e9 / peak) if traffic else None
+    del env, shards, actions
+    torch.cuda.empty_cache()
+    return out
+
+
+def pcie_ceiling(device, dist=None, mbytes=256, reps=6):
+    """What this box gives plain pinned cudaMemcpyAsync traffic, all ranks at once: D2H and H2D copies
+    of `mbytes` MiB running concurrently on two streams (torch copy_ = one cudaMemcpyAsync each).
+    Returns GB/s per GPU (d2h, h2d) -- the ceiling of the e2e number, which moves 22 B out and 4 B in
+    per CartPole env-step."""
+    import torch
+
+    n = mbytes << 20
+    d_out = torch.empty(n, dtype=torch.uint8, device=device)
+    d_in = torch.empty(n // 4, dtype=torch.uint8, device=device)
+    h_out = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+    h_in = torch.empty(n // 4, dtype=torch.uint8, pin_memory=True)
+    s1, s2 = torch.cuda.Stream(device=device), torch.cuda.Stream(device=device)
+    best = None
+    for rep in range(reps):
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        t0 = time.perf_counter()
+        with torch.cuda.stream(s1):
+            h_out.copy_(d_out, non_blocking=True)
+        with torch.cuda.stream(s2):
+            d_in.copy_(h_in, non_blocking=True)
+        s1.synchronize()
+        s2.synchronize()
+        dt = time.perf_counter() - t0
+        if rep and (best is None or dt < best):
+            best = dt
+    return n / best / 1e9, (n // 4) / best / 1e9
+
+
+def bind_to_gpu_numa_node(local_rank):
+    """Pin this rank's threads (and with them the first-touch placement of its pinned host buffers) to
+    the CPU set NVML reports as local to its GPU.  Returns a short description for the bench line."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local_rank)
+        n_words = (os.cpu_count() + 63) // 64
+        mask = pynvml.nvmlDeviceGetCpuAffinity(h, n_words)
+        cpus = {64 * w + b for w, word in enumerate(mask) for b in range(64) if (word >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        use = cpus & allowed
+        if use and use != allowed:
+            os.sched_setaffinity(0, use)
+            return f"bound to {len(use)} CPUs local to GPU {local_rank} (NVML affinity)"
+        return f"NVML affinity of GPU {local_rank} = all {len(allowed)} allowed CPUs (single NUMA domain visible)"
+    except Exception as e:          # no NVML / not permitted: run unbound
+        return f"unbound ({type(e).__name__})"
 
 
 def run_gpu(args):
@@ -414,6 +531,7 @@ def run_gpu(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa_note = bind_to_gpu_numa_node(local)      # before any pinned allocation: first touch decides the node
     torch.cuda.set_device(local)
     dist = None
     if world > 1:
@@ -439,11 +557,10 @@ def run_gpu(args):
         sampler.start()
     # ---- device-resident throughput ----
     launches0 = env.launch_count
-    # long enough for the clock sampler to see the timed region
     sampler.mark(0)
     rollout_k = int(wl.get("rollout_k", 0))
     per_launch = max(rollout_k, 1)                     # env-steps each env advances per launch
-    secs = time_steps(shards, actions, args.steps, max(args.warmup, 3), dist, rollout_k, args.rollout_policy)
+    secs, seg = time_steps(shards, actions, args.steps, max(args.warmup, 3), dist, rollout_k, args.rollout_policy)
     launches = env.launch_count - launches0 - max(args.warmup, 3) * len(shards)
     t = torch.tensor([secs], dtype=torch.float64, device=dev)
     if dist is not None:
@@ -452,38 +569,39 @@ def run_gpu(args):
     total_steps = world * n_envs * args.steps * per_launch
     value = total_steps / secs_max
     # ---- roofline for the (only) kernel of the step ----
-    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
-    if os.path.exists(peaks_path):
-        with open(peaks_path) as f:
-            peak, peak_src = float(json.load(f)["hbm_gbs"]), "MEASURED_PEAKS.json hbm_gbs (measured copy)"
-    else:
-        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    peak, peak_src = load_peak()
     launch_s = secs / args.steps                       # this rank's average step duration
+    seg_sorted = sorted(seg)
+    launch_med = seg_sorted[len(seg_sorted) // 2]      # median of the 5 repetitions
     bytes_per_launch_env = env.bytes_per_step
     if rollout_k:
         # K fused steps move state / theta / t once per launch and write the return + length
         # accumulators: (2 S w + 2 P w + 8) + 12 per env per launch
         bytes_per_launch_env = env.bytes_per_step - (shards[0].buffers["action"].element_size() + 4 + 1 + 1) + 12 + 6
     achieved = bytes_per_launch_env * n_envs / launch_s / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        with open(tpath) as f:
-            traffic = json.load(f).get(args.workload)
+    traffic = load_traffic().get(args.workload)
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "traffic_unit": "DRAM bytes per step (ncu --set full, profiles/traffic.json)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_env_step": bytes_per_launch_env / per_launch,
-                "kernel_us_per_launch": launch_s * 1e6 / len(shards)}
+                "kernel_us_per_launch": launch_s * 1e6 / len(shards),
+                "kernel_us_per_launch_median_of_5": launch_med * 1e6 / len(shards),
+                "kernel_us_per_launch_repetitions": [x * 1e6 / len(shards) for x in seg]}
     if traffic and not rollout_k:
-        # the measured DRAM rate next to the algorithmic one: gridworld kernels write a distribution
-        # back only when its update fired, so with a rare scheduler (C2) the traffic is well below
-        # SURVEY 8(d)'s figure (which counts theta read + write every step) and frac can exceed 1
+        # the measured DRAM rate next to the algorithmic one
         roofline["dram_gbs_from_traffic"] = traffic / launch_s / 1e9
+        roofline["frac_physical"] = traffic / launch_s / 1e9 / peak
         if traffic < 0.9 * bytes_per_launch_env * n_envs:
-            roofline["note"] = ("DRAM traffic is below the algorithmic bytes: unchanged theta planes are not "
-                                "written back (gridworld kernels), so achieved (algorithmic bytes / time) can "
-                                "exceed the copy peak; dram_gbs_from_traffic is the physical rate")
+            # gridworld kernels write a distribution back only when its update fired, so with a rare
+            # scheduler (C2) the traffic is well below SURVEY 8(d)'s figure (which counts theta read + write
+            # every step) and the algorithmic rate can exceed the copy peak: frac is the PHYSICAL rate there
+            roofline["frac_algorithmic"] = roofline["frac"]
+            roofline["achieved_algorithmic"] = achieved
+            roofline["achieved"] = roofline["dram_gbs_from_traffic"]
+            roofline["frac"] = roofline["frac_physical"]
+            roofline["note"] = ("DRAM traffic is below the algorithmic bytes (unchanged theta planes are not written "
+                                "back): achieved / frac are the physical DRAM rate (ncu traffic / CUDA-event time); "
+                                "*_algorithmic keep SURVEY 8(d)'s formula")
     if len(shards) > 1:
         roofline["note"] = ("heterogeneous batch: one launch per env kind per step; bytes include the per-env row "
                             "words read each step: " +
@@ -521,6 +639,11 @@ def run_gpu(args):
     for s, (h_act, h_out) in zip(shards, host_io):
         a_, b_ = s.host_bytes_per_step(h_act, h_out)
         h2d, d2h = h2d + a_, d2h + b_
+    # what the box gives plain pinned copies, all ranks at once: the ceiling of the e2e number
+    ceil_d2h, ceil_h2d = pcie_ceiling(dev, dist)
+    cvec = torch.tensor([ceil_d2h, ceil_h2d], dtype=torch.float64, device=dev)
+    if dist is not None:
+        dist.all_reduce(cvec, op=dist.ReduceOp.SUM)
     # ---- metric reduction over NCCL (the only collective on this path) ----
     stats = torch.stack([sum(s.buffers["reward"].double().sum() for s in shards),
                          sum(((s.buffers["flags"] & 3) != 0).double().sum() for s in shards),
@@ -528,10 +651,25 @@ def run_gpu(args):
     if dist is not None:
         dist.all_reduce(stats, op=dist.ReduceOp.SUM)
     sampler.stop()
+    # ---- the other BASELINE configs, briefly (rank 0, single GPU): roofline.workloads ----
+    table = None
+    if world == 1 and not args.no_table and args.workload == "c1_cartpole":
+        del host_io, actions, shards, env
+        torch.cuda.empty_cache()
+        table = {args.workload: {"steps_per_s": value, "us_per_launch": launch_med * 1e6,
+                                 "frac_algorithmic": achieved / peak,
+                                 "frac_physical": (traffic / launch_med / 1e9 / peak) if traffic else None,
+                                 "envs": n_envs, "launches_per_step": 1}}
+        for name in TABLE_WORKLOADS:
+            table[name] = quick_measure(name, rank, args.seed)
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             cpu = cpu_baseline(wl["case"])
+            cpu["port_vs_reference"] = port_vs_reference(wl["case"])
+        if table is not None:
+            roofline["workloads"] = table
+        e2e_gbs = e2e_value * (h2d + d2h) / (world * n_envs) / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * secs_max / args.steps,
@@ -539,20 +677,27 @@ def run_gpu(args):
             "dtype": "f32" if wl["precision"] == "fp32" else "f64", "data": "synthetic",
             "config": {
                 "workload": args.workload, "case": wl["case"],
-                "env_id": "+".join(s.program.env_id for s in shards),
+                "env_id": case["env_id"] if not wl.get("hetero") else "CartPole-v1+FrozenLake-v1",
                 "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
                 "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k, "rollout_policy": args.rollout_policy if rollout_k else None,
                 "kernels": "general" if args.general_kernels else "lean where the program allows",
                 "parallelism": f"env-shard x{world}, no data-path collective",
-                "l2_policy": f"working set {env.bytes_per_step * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
+                "l2_policy": f"working set {bytes_per_launch_env * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
-                "launches_per_step": len(shards),
+                "launches_per_step": 1 if not wl.get("hetero") else 2,
+                "timing": "CUDA events around exactly `steps` launches; 5 repetitions by intermediate events",
             },
             "roofline": roofline,
             "cpu_baseline": cpu,
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "steps": e2e_steps, "chunks": args.chunks,
-                    "api": "nsgym_step_host (C ABI, pinned host buffers, H2D actions + D2H obs/reward/flags/change)"},
+                    "api": "nsgym_step_host (C ABI, pinned host buffers, H2D actions + D2H obs/reward/flags/change)",
+                    "gbs": e2e_gbs,
+                    "pcie_ceiling_gbs": {"d2h": float(cvec[0]), "h2d": float(cvec[1]),
+                                         "how": "plain pinned cudaMemcpyAsync, D2H + H2D (4:1 bytes) concurrently on "
+                                                "two streams, all ranks at once, summed over ranks"},
+                    "frac_of_pcie_ceiling": e2e_gbs / float(cvec[0] + cvec[1]),
+                    "host_binding": numa_note},
             "gpu_launches": launches,
             "clocks": sampler.summary(),
             "batch_stats": {"mean_reward_last_step": float(stats[0] / stats[2]),
@@ -562,6 +707,16 @@ def run_gpu(args):
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def port_vs_reference(case_name):
+    """Speed of the oracle port relative to the REAL reference on the same case, measured in the build
+    container (tools/port_vs_reference.py; the reference cannot run on the GPU box)."""
+    path = os.path.join(ROOT, "profiles", "port_vs_reference.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        return json.load(f).get(case_name)
 
 
 def main():
@@ -576,6 +731,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=30, dest="e2e_steps")
     ap.add_argument("--chunks", type=int, default=8)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-table", action="store_true", dest="no_table",
+                    help="skip the brief timing of the other BASELINE configs (roofline.workloads)")
     ap.add_argument("--rollout-policy", default="random", choices=["random", "linear", "linear_per_env"],
                     dest="rollout_policy", help="device-side policy of the *_rollout* workloads")
     ap.add_argument("--general-kernels", action="store_true", dest="general_kernels",

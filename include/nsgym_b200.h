@@ -239,6 +239,11 @@ int nsgym_reset(NsgymHandle* h, const uint8_t* d_mask, const double* d_inj_unifo
 int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform,
                const double* d_inj_normal, int skip_updates, void* stream);
 
+/* One host call for a logical batch made of several handles (BASELINE config C4: CartPole + FrozenLake
+ * envs with per-env rows are bucketed by env kind, one handle per kind): steps every handle on `stream`,
+ * back to back.  d_actions[k] NULL (or d_actions NULL) = handle k's bound staging buffer. */
+int nsgym_step_many(NsgymHandle* const* handles, const void* const* d_actions, int n, int skip_updates, void* stream);
+
 /* Result packaging of NSWrapper.step (base.py:314-361) for the batch, in one launch: splits the
  * flag / change-mask / time words the step left in the bound buffers into what the wrapper
  * returns -- d_terminated, d_truncated, d_was_reset uint8[N] (0 / 1), d_relative_time int32[N],

@@ -458,6 +458,20 @@ int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform
   return 0;
 }
 
+int nsgym_step_many(NsgymHandle* const* handles, const void* const* d_actions, int n, int skip_updates, void* stream) {
+  if (!handles || n <= 0) return fail(-1, "no handles");
+  for (int k = 0; k < n; ++k) {
+    if (!handles[k] || !handles[k]->bound) return fail(-1, "handle %d not bound", k);
+    if (!handles[k]->initialised) return fail(-4, "handle %d: step before reset", k);
+  }
+  // back-to-back launches from one host call: a batch of several env kinds (BASELINE config C4) pays the
+  // host-side cost of a step once, and the kernels queue without gaps
+  for (int k = 0; k < n; ++k)
+    if (int rc = nsgym_step(handles[k], d_actions ? d_actions[k] : nullptr, nullptr, nullptr, skip_updates, stream))
+      return rc;
+  return 0;
+}
+
 int nsgym_unpack(NsgymHandle* h, uint8_t* d_terminated, uint8_t* d_truncated, uint8_t* d_was_reset,
                  int32_t* d_relative_time, uint8_t* d_env_change, void* stream) {
   if (!h || !h->bound) return fail(-1, "handle not bound");

@@ -102,7 +102,7 @@ class NsgymSnapshotInfo(C.Structure):
 
 EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
-    "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_unpack", "nsgym_episode_stats", "nsgym_step_host", "nsgym_alloc_host", "nsgym_free_host",
+    "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_step_many", "nsgym_unpack", "nsgym_episode_stats", "nsgym_step_host", "nsgym_alloc_host", "nsgym_free_host",
     "nsgym_rollout", "nsgym_rollout_linear", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_eval_w1", "nsgym_eval_draws", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
     "nsgym_launch_count", "nsgym_last_kernel_class",
 ]
@@ -154,6 +154,7 @@ def load(build_if_missing: bool = False):
     lib.nsgym_bind.argtypes = [C.c_void_p, C.POINTER(NsgymBuffers)]
     lib.nsgym_reset.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsgym_step.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+    lib.nsgym_step_many.argtypes = [C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_void_p]
     lib.nsgym_unpack.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsgym_episode_stats.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.nsgym_step_host.argtypes = [C.c_void_p, C.c_void_p, C.POINTER(NsgymHostOut), C.c_int, C.c_void_p]

@@ -585,8 +585,16 @@ class MixedVectorEnv:
         return [s.reset(seed=seed, **kw) for s in self.shards]
 
     def step_raw(self, actions=None):
-        for k, s in enumerate(self.shards):
-            s.step_raw(None if actions is None else actions[k])
+        """One host call (``nsgym_step_many``) steps every shard, back to back on the current stream."""
+        n = len(self.shards)
+        handles = (C.c_void_p * n)(*[s._h for s in self.shards])
+        acts = (C.c_void_p * n)(*[None if actions is None or actions[k] is None else actions[k].data_ptr()
+                                  for k in range(n)])
+        s0 = self.shards[0]
+        if any(s.skip_updates != s0.skip_updates or s.device != s0.device for s in self.shards):
+            raise ValueError("the shards of a mixed batch share one device and one planning mode")
+        with torch.cuda.device(s0.device):
+            nv.check(s0.lib.nsgym_step_many(handles, acts, n, int(s0.skip_updates), s0._stream()), "nsgym_step_many")
 
     def step(self, actions):
         return [s.step(a) for s, a in zip(self.shards, actions)]

@@ -181,3 +181,28 @@ def test_host_memory_helpers_and_error_paths():
     env.step_host(h_act, h_out, n_chunks=1000)         # more chunks than 256-env blocks: clamps
     torch.cuda.synchronize()
     assert torch.equal(h_out["obs"], env.buffers["obs"].cpu())
+
+
+def test_mixed_batch_steps_all_shards_in_one_call():
+    """MixedVectorEnv.step_raw (nsgym_step_many) == stepping every shard on its own."""
+    import torch
+
+    from ns_gym_b200.vector_env import MixedVectorEnv
+
+    names = ("c4_cartpole_rows", "c4_frozenlake8_rows")
+    one = [pu.gpu_env(CASES[n], 300, precision="fp32", seed=4) for n in names]
+    many = [pu.gpu_env(CASES[n], 300, precision="fp32", seed=4) for n in names]
+    mixed = MixedVectorEnv(many)
+    for e in one:
+        e.reset()
+    mixed.reset()
+    for k in range(25):
+        acts = [e.action_space.sample() for e in one]
+        for e, a in zip(one, acts):
+            e.step_raw(a)
+        mixed.step_raw(acts)
+    torch.cuda.synchronize()
+    for a, b in zip(one, many):
+        for key in ("state", "theta", "t", "reward", "flags", "change"):
+            assert torch.equal(a.buffers[key], b.buffers[key]), key
+    assert mixed.launch_count == sum(e.launch_count for e in one)

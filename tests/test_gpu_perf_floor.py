@@ -1,0 +1,51 @@
+"""GPU: throughput floors for every BASELINE config (C1-C5), so that the numbers quoted in DESIGN.md /
+BASELINE.md are checked by the driver's own `pytest -m gpu` run and not only by the builder.
+
+Each workload is timed at its bench batch size with CUDA events (bench.quick_measure: 5 warm-up + 30
+timed launches in 5 repetitions, median) and must reach 90 % of the value recorded in
+tests/perf_floors.json; single-step workloads with an ncu traffic figure (profiles/traffic.json) must
+also reach 90 % of the physical-DRAM fraction that value implies.  A throttled GPU (hw slowdown,
+thermal slowdown) invalidates the measurement: the test then skips instead of failing."""
+import json
+import os
+import subprocess
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+with open(os.path.join(HERE, "perf_floors.json")) as f:
+    FLOORS = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+
+
+def _throttle_reasons():
+    q = ("clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks.sm,clocks.max.sm")
+    try:
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", "0"],
+                             capture_output=True, text=True, timeout=20).stdout.strip().split(",")
+        return [n for n, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"), out)
+                if v.strip().lower().startswith("active")]
+    except Exception:
+        return []
+
+
+@pytest.mark.parametrize("workload", sorted(FLOORS))
+def test_workload_reaches_its_floor(workload):
+    import bench
+
+    got = bench.quick_measure(workload)
+    reasons = _throttle_reasons()
+    if reasons:
+        pytest.skip(f"GPU throttled during the measurement: {reasons}")
+    want = FLOORS[workload]
+    assert got["steps_per_s"] >= 0.9 * want, (
+        f"{workload}: {got['steps_per_s']:.3e} env-steps/s < 90 % of the recorded {want:.3e} "
+        f"({got['us_per_launch']:.1f} us per launch)")
+    if got.get("frac_physical") is not None:
+        peak, _ = bench.load_peak()
+        traffic = bench.load_traffic()[workload]
+        implied = traffic * want / (got["envs"] * 1e9) / peak          # physical fraction at the recorded rate
+        assert got["frac_physical"] >= 0.9 * implied
+        assert got["frac_physical"] < 1.05, "faster than the measured copy peak: the kernel is not doing the work"

@@ -6,7 +6,7 @@ mkdir -p gpurun_out/bench_all
 WL=${@:-"c1_cartpole c1_cartpole_fp64 c2_frozenlake8 c2_frozenlake8_16m c3_acrobot c3_acrobot_fp64 c3_mountaincar c3_mountaincar_fp64 c3_pendulum c3_pendulum_fp64 c4_hetero c5_bridge c5_bridge_rollout32 c5_bridge_rollout100 c5_bridge_split_rollout32 c1_cartpole_rollout32 c3_acrobot_rollout32 c3_acrobot_fp64_rollout32"}
 for W in $WL; do
   S=400; case $W in *rollout100) S=20;; *rollout*) S=50;; esac
-  python bench.py --workload $W --steps $S --warmup 20 --no-cpu-baseline --e2e-steps 5 > gpurun_out/bench_all/$W.log 2> gpurun_out/bench_all/$W.err
+  python bench.py --workload $W --steps $S --warmup 20 --no-cpu-baseline --no-table --e2e-steps 5 > gpurun_out/bench_all/$W.log 2> gpurun_out/bench_all/$W.err
 done
 python - <<'PY'
 import json, glob
