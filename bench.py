@@ -669,7 +669,7 @@ def run_gpu(args):
             cpu["port_vs_reference"] = port_vs_reference(wl["case"])
         if table is not None:
             roofline["workloads"] = table
-        e2e_gbs = e2e_value * (h2d + d2h) / (world * n_envs) / 1e9
+        e2e_gbs = e2e_value * (h2d + d2h) / n_envs / 1e9      # aggregate: h2d / d2h are this rank's bytes per step
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": 1e3 * secs_max / args.steps,
