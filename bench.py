@@ -550,6 +550,9 @@ def run_gpu(args):
     if args.general_kernels:        # the general (all rule classes, injection-capable) instantiations
         for s in shards:
             s.set_option("general_kernels", 1)
+    if args.no_specialize:          # the precompiled lean kernels instead of the program-specialised ones
+        for s in shards:
+            s.set_option("specialize", 0)
     env.reset(seed=args.seed)
     actions = [random_actions(s, 1234 + rank + 17 * k) for k, s in enumerate(shards)]
     sampler = ClockSampler(local)
@@ -680,7 +683,10 @@ def run_gpu(args):
                 "env_id": case["env_id"] if not wl.get("hetero") else "CartPole-v1+FrozenLake-v1",
                 "envs_per_gpu": n_envs, "global_envs": world * n_envs, "precision": wl["precision"],
                 "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k, "rollout_policy": args.rollout_policy if rollout_k else None,
-                "kernels": "general" if args.general_kernels else "lean where the program allows",
+                "kernels": "general" if args.general_kernels else (
+                    "program-specialised (NVRTC at first launch, nsgym_jit.cu)"
+                    if all(getattr(s, "last_kernel_specialized", False) for s in shards)
+                    else "precompiled lean where the program allows"),
                 "parallelism": f"env-shard x{world}, no data-path collective",
                 "l2_policy": f"working set {bytes_per_launch_env * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "
                              "(inputs larger than L2, no flush needed)",
@@ -735,6 +741,8 @@ def main():
                     help="skip the brief timing of the other BASELINE configs (roofline.workloads)")
     ap.add_argument("--rollout-policy", default="random", choices=["random", "linear", "linear_per_env"],
                     dest="rollout_policy", help="device-side policy of the *_rollout* workloads")
+    ap.add_argument("--no-specialize", action="store_true", dest="no_specialize",
+                    help="keep the precompiled lean kernels (no run-time specialisation of the step kernel)")
     ap.add_argument("--general-kernels", action="store_true", dest="general_kernels",
                     help="launch the general kernel instantiations instead of the lean ones (kernel experiments)")
     args = ap.parse_args()

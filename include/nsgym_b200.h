@@ -378,9 +378,27 @@ int nsgym_eval_draws(NsgymHandle* h, int what, int lane, int t, double p, uint64
 /* Handle options.  NSGYM_OPT_GENERAL_KERNELS != 0: always launch the general kernel instantiations
  * (all rule classes, injection-capable) instead of the lean ones the library would pick for this
  * program -- same results (bit for bit in fp64 mode), used by the tests to tie the lean kernels to
- * the oracle-checked general ones. */
-enum { NSGYM_OPT_GENERAL_KERNELS = 1 };
+ * the oracle-checked general ones.
+ * NSGYM_OPT_SPECIALIZE: program-specialised kernels.  A handle whose program stays in the lean classes
+ * can run a step kernel compiled at run time (NVRTC, ~0.3 s once per distinct program in the process) from
+ * the library's own device code with the lowered program as a compile-time constant: the interpreter's
+ * constant-bank loads, uniform branches, range / modulo tests and select masks fold away.  Same results as
+ * the precompiled lean kernel (bit for bit in fp64 mode; fp32 may differ in the last bit where the folded
+ * constants change an FMA contraction).  -1 (default): batches of >= 32768 envs; 0: never; 1: always.
+ * Environment: NSGYM_B200_NO_JIT=1 disables it process-wide, NSGYM_B200_NVRTC names libnvrtc.so.12,
+ * NSGYM_B200_JIT_VERBOSE=1 prints why a specialisation was not possible (the precompiled kernel runs then). */
+enum { NSGYM_OPT_GENERAL_KERNELS = 1, NSGYM_OPT_SPECIALIZE = 2 };
 int nsgym_set_option(NsgymHandle* h, int option, int64_t value);
+/* 1 when the handle's last step / rollout launch went to a program-specialised kernel */
+int nsgym_last_kernel_specialized(const NsgymHandle* h);
+/* Generate and compile (no device needed) the specialised step kernel of `spec` as a handle with / without
+ * delta and float32-observation buffers would run it; copies the source and the compiler log out when
+ * asked.  Returns the cubin size, -2 when the program does not specialise, -3 when NVRTC is missing or the
+ * compilation fails (nsgym_last_error says which). */
+int nsgym_jit_check(const NsgymSpec* spec, int want_delta, int want_obs, char* source, size_t source_len, char* log,
+                    size_t log_len);
+/* process-wide counters of the specialiser; returns 1 when it is enabled */
+int nsgym_jit_stats(int64_t* compiled, int64_t* hits, int64_t* failed, char* last_failure, size_t len);
 
 /* replaces: reset(seed=...) reseeding (base.py:386-388, 412-421): re-keys the Philox streams */
 void nsgym_set_seed(NsgymHandle* h, uint64_t seed);

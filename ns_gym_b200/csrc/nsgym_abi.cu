@@ -5,6 +5,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <vector>
 
 #include "nsgym_host.h"
 
@@ -29,6 +30,9 @@ int fail(int code, const char* fmt, ...) {
   } while (0)
 
 constexpr int kHostStreams = 4;
+// NSGYM_OPT_SPECIALIZE auto: the ~0.3 s NVRTC compilation pays for itself on throughput-sized batches; a
+// small batch is launch-latency bound either way and keeps the precompiled kernel
+constexpr int64_t kSpecializeMinEnvs = 32768;
 
 struct KindInfo { int state_words, obs_words, n_theta; bool box; };
 const KindInfo kKinds[NSGYM_ENV_COUNT] = {
@@ -54,6 +58,9 @@ struct NsgymHandle {
   int32_t plan_elapsed = -1;       // planning copy (nsgym_fanout): TimeLimit steps since the copy
   int32_t general_kernels = 0;     // NSGYM_OPT_GENERAL_KERNELS
   int32_t kernel_class = -1;       // instantiation picked by the last step / rollout launch (NSGYM_KERNEL_*)
+  int32_t specialize = -1;         // NSGYM_OPT_SPECIALIZE: -1 auto (batches of >= kSpecializeMinEnvs envs), 0 never, 1 always
+  int32_t specialized = 0;         // the last step / rollout launch went to a program-specialised kernel
+  nsg::SpecCache spec_cache;       // program-specialised kernels of this handle (nsgym_jit.cu)
 
   bool grid() const { return nsg::is_grid_kind(spec.env_kind); }
   size_t real_bytes() const { return grid() ? 8 : (spec.precision == NSGYM_F64 ? 8 : 4); }
@@ -79,6 +86,8 @@ nsg::LaunchIO base_io(const NsgymHandle* h) {
   io.plan_elapsed = h->plan_elapsed;
   io.general_kernels = h->general_kernels;
   io.sched_replay = h->spec.persistent_params ? 0 : 1;
+  io.specialize = nsg::jit::enabled() && (h->specialize > 0 || (h->specialize < 0 && h->spec.n_envs >= kSpecializeMinEnvs));
+  io.spec_cache = const_cast<nsg::SpecCache*>(&h->spec_cache);
   return io;
 }
 
@@ -86,8 +95,13 @@ cudaError_t dispatch(NsgymHandle* h, nsg::LaunchOp op, const nsg::LaunchIO& io_i
   h->launches += 1;
   nsg::LaunchIO io = io_in;
   int32_t cls = -1;
+  int32_t spec = 0;
   io.kernel_class = &cls;
-  struct Keep { NsgymHandle* h; nsg::LaunchOp op; int32_t* c; ~Keep() { if (op != nsg::OP_RESET && *c >= 0) h->kernel_class = *c; } } keep{h, op, &cls};
+  io.specialized = &spec;
+  struct Keep {
+    NsgymHandle* h; nsg::LaunchOp op; int32_t* c; int32_t* s;
+    ~Keep() { if (op != nsg::OP_RESET && *c >= 0) { h->kernel_class = *c; h->specialized = *s; } }
+  } keep{h, op, &cls, &spec};
   if (h->grid()) return nsg::launch_grid(op, h->spec, h->pools, io, s);
   if (h->spec.precision == NSGYM_F64) return nsg::launch_classic_f64(op, h->spec, h->pools, io, s);
   return nsg::launch_classic_f32(op, h->spec, h->pools, io, s);
@@ -810,6 +824,7 @@ int nsgym_set_option(NsgymHandle* h, int option, int64_t value) {
   if (!h) return fail(-1, "NULL handle");
   switch (option) {
     case NSGYM_OPT_GENERAL_KERNELS: h->general_kernels = value != 0; return 0;
+    case NSGYM_OPT_SPECIALIZE: h->specialize = value < 0 ? -1 : (value != 0); return 0;
     default: return fail(-1, "unknown option %d", option);
   }
 }
@@ -819,5 +834,47 @@ uint64_t nsgym_step_index(const NsgymHandle* h) { return h ? h->step_index : 0; 
 void nsgym_set_step_index(NsgymHandle* h, uint64_t v) { if (h) h->step_index = v; }
 int64_t nsgym_launch_count(const NsgymHandle* h) { return h ? h->launches : 0; }
 int nsgym_last_kernel_class(const NsgymHandle* h) { return h ? h->kernel_class : -1; }
+int nsgym_last_kernel_specialized(const NsgymHandle* h) { return h ? h->specialized : 0; }
+
+int nsgym_jit_check(const NsgymSpec* spec, int want_delta, int want_obs, char* source, size_t source_len, char* log,
+                    size_t log_len) {
+  if (int rc = validate(spec)) return rc;
+  NsgymSpec s = *spec;   // as nsgym_create keeps it (no device needed up to here)
+  for (int j = 0; j < s.n_slots; ++j) nsg::set_mod_magic(&s.slots[j], *spec);
+  nsg::LaunchIO io{};
+  io.n = io.count = s.n_envs > 0 ? s.n_envs : 1;
+  io.seed = s.seed;
+  io.plan_elapsed = -1;
+  io.sched_replay = s.persistent_params ? 0 : 1;
+  // non-NULL markers only: the generator tests the pointers, nothing dereferences them
+  static float marker[2];
+  if (want_delta) io.delta = marker;
+  if (want_obs) io.obs = marker;
+  std::string src;
+  io.spec_source = &src;
+  const nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr};
+  cudaError_t e;
+  if (nsg::is_grid_kind(s.env_kind)) return fail(-2, "gridworld programs do not specialise yet");
+  if (s.precision == NSGYM_F64) e = nsg::launch_classic_f64(nsg::OP_STEP, s, pools, io, nullptr);
+  else e = nsg::launch_classic_f32(nsg::OP_STEP, s, pools, io, nullptr);
+  if (e != cudaSuccess || src.empty()) return fail(-2, "this program does not specialise (general kernel class or per-env rows)");
+  if (source && source_len) { std::strncpy(source, src.c_str(), source_len - 1); source[source_len - 1] = 0; }
+  std::vector<char> cubin;
+  std::string text;
+  const bool fmad = !nsg::is_grid_kind(s.env_kind) && s.precision != NSGYM_F64;
+  const int rc = nsg::jit::compile(src, fmad, &cubin, &text);
+  if (log && log_len) { std::strncpy(log, text.c_str(), log_len - 1); log[log_len - 1] = 0; }
+  if (rc != 0) return fail(-3, "specialised kernel does not compile: %.400s", text.c_str());
+  return int(cubin.size());
+}
+
+int nsgym_jit_stats(int64_t* compiled, int64_t* hits, int64_t* failed, char* last_failure, size_t len) {
+  const nsg::jit::Stats st = nsg::jit::stats();
+  if (compiled) *compiled = st.compiled;
+  if (hits) *hits = st.hits;
+  if (failed) *failed = st.failed;
+  if (last_failure && len) { std::strncpy(last_failure, st.last_failure.c_str(), len - 1); last_failure[len - 1] = 0; }
+  return nsg::jit::enabled() ? 1 : 0;
+}
 
 }  // extern "C"

@@ -2,6 +2,7 @@
 // once per precision (nsgym_f32.cu with FMA contraction, nsgym_f64.cu with -fmad=false).
 #pragma once
 #include <limits>
+#include <string>
 #include <type_traits>
 #include <utility>
 
@@ -206,6 +207,30 @@ static StepIO<R> build_io(const LaunchIO& a) {
   return io;
 }
 
+// Source of the program-specialised single-step kernel of a lean program (nsgym_jit.cu): the body the
+// precompiled kernel runs (classic_step_body), with the lowered program rebuilt as a constexpr object
+// from the words of the host's ProgramHeadT and the launch facts fixed in SpecFix.
+template <typename R, int KIND, int NP>
+static std::string spec_step_source(const ProgramT<R, NP>& P, int level, const StepIO<R>& io, bool root) {
+  const char* real = std::is_same<R, float>::value ? "float" : "double";
+  const ProgramHeadT<R, NP>& head = P;
+  static_assert(sizeof(ProgramHeadT<R, NP>) % 4 == 0, "program head is a whole number of words");
+  const std::string prog = std::string("ProgramT<") + real + ", " + std::to_string(NP) + ">";
+  const std::string headt = std::string("ProgramHeadT<") + real + ", " + std::to_string(NP) + ">";
+  std::string s = "#include \"nsgym_device.cuh\"\nnamespace nsg {\ntemplate <int N> struct SpecWords { uint32_t w[N]; };\n";
+  s += "struct SpecFix { static constexpr int prefetch = " + std::to_string(io.prefetch ? 1 : 0) +
+       ", want_delta = " + std::to_string(io.delta ? 1 : 0) + ", has_obs = " + std::to_string(io.obs ? 1 : 0) +
+       ", root = " + std::to_string(root ? 1 : -1) + "; };\n";
+  s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n  static_cast<" + headt +
+       "&>(P) = __builtin_bit_cast(" + headt + ", SpecWords<" + std::to_string(sizeof(head) / 4) + ">{{" +
+       jit::words(&head, sizeof(head)) + "}});\n  return P;\n}\n}  // namespace nsg\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::classic_min_blocks<" + std::string(real) + ", " +
+       std::to_string(KIND) + ", " + std::to_string(level) + ">())\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<" +
+       real + "> io) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n  nsg::classic_step_body<" + real + ", " +
+       std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", nsg::SpecFix>(P, io);\n}\n";
+  return s;
+}
+
 template <typename R, int KIND, int NP>
 static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,
                                       const LaunchIO& a, cudaStream_t stream) {
@@ -248,6 +273,25 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   if (a.kernel_class) *a.kernel_class = level == 2 ? NSGYM_KERNEL_GENERAL : (level == 1 ? NSGYM_KERNEL_LEAN_MEDIUM : NSGYM_KERNEL_LEAN_FAST);
   constexpr bool kHasMedium = true;
   const unsigned lean_grid = unsigned((a.count + block * NSGYM_LEAN_EPT - 1) / (block * NSGYM_LEAN_EPT));
+  if (a.specialized) *a.specialized = 0;
+  if (op == OP_STEP && level < 2 && (a.specialize || a.spec_source)) {
+    // lean program: the kernel compiled for exactly this program (cached per distinct source)
+    const bool root = a.plan_elapsed < 0 && !a.skip_updates;
+    const uint32_t facts = uint32_t(level) | (io.prefetch ? 4u : 0u) | (io.delta ? 8u : 0u) | (io.obs ? 16u : 0u) |
+                           (root ? 32u : 0u);
+    cudaKernel_t k = nullptr;
+    if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
+      const std::string src = spec_step_source<R, KIND, NP>(P, level, io, root);
+      if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
+      k = jit::kernel(src, std::is_same<R, float>::value, nullptr);
+      if (a.spec_cache) a.spec_cache->put(facts, k);
+    }
+    if (k) {
+      void* args[] = {const_cast<StepIO<R>*>(&io)};
+      if (a.specialized) *a.specialized = 1;
+      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(lean_grid), dim3(block), args, 0, stream);
+    }
+  }
   switch (op) {
     case OP_STEP:
       if (level == 2) classic_step_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io);

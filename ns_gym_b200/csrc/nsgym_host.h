@@ -3,6 +3,10 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <string>
+#include <utility>
+#include <vector>
+
 #include "nsgym_b200.h"
 
 namespace nsg {
@@ -54,7 +58,35 @@ struct LaunchIO {
   const void* policy; int32_t policy_per_env;   // linear (float) / tabular (uint8) rollout policy, NULL = uniform random
   const RowTable* rows;   // heterogeneous handles
   int32_t* kernel_class;  // out (host, may be NULL): which instantiation the launcher picked (NSGYM_KERNEL_*)
+  int32_t specialize;     // lean programs: launch the program-specialised kernel (nsgym_jit.cu) when it can be built
+  int32_t* specialized;   // out (host, may be NULL): 1 when the launch went to a program-specialised kernel
+  std::string* spec_source;   // test entry (nsgym_jit_check): receive the generated source instead of launching
+  struct SpecCache* spec_cache;   // per-handle memo of the specialised kernels (the program of a handle never changes)
 };
+
+// launch facts -> kernel (NULL = could not be built: keep the precompiled kernel); owned by the handle
+struct SpecCache {
+  std::vector<std::pair<uint32_t, cudaKernel_t>> slots;
+  bool find(uint32_t key, cudaKernel_t* k) const {
+    for (const auto& s : slots)
+      if (s.first == key) { *k = s.second; return true; }
+    return false;
+  }
+  void put(uint32_t key, cudaKernel_t k) { slots.emplace_back(key, k); }
+};
+
+// Program-specialised kernels (nsgym_jit.cu): the device headers compiled again at run time by NVRTC with
+// the handle's lowered program as a compile-time constant.
+namespace jit {
+bool enabled();                                           // false when NSGYM_B200_NO_JIT is set
+std::string words(const void* p, size_t bytes);           // a pointer-free object as 32-bit literals "0x..u,0x..u,..."
+// compile to an sm_100a cubin (needs NVRTC, no device); 0 or a negative status with `log` filled
+int compile(const std::string& source, bool fmad, std::vector<char>* cubin, std::string* log);
+// compiled (once per distinct source in the process) and loaded kernel `nsgym_spec_kernel`, or NULL with `why`
+cudaKernel_t kernel(const std::string& source, bool fmad, std::string* why);
+struct Stats { int64_t compiled = 0, hits = 0, failed = 0; std::string last_failure; };
+Stats stats();
+}  // namespace jit
 
 // each returns cudaError_t of the launch (cudaGetLastError)
 cudaError_t launch_classic_f32(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools,

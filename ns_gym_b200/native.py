@@ -33,6 +33,7 @@ UPD_D_TARGET, UPD_D_LERP, UPD_D_STEPWISE, UPD_D_CYCLIC, UPD_D_RANDOM = 36, 37, 3
 CONS_NONE, CONS_REJECT_LE0, CONS_REJECT_LT0, CONS_ACRO_LENGTH1, CONS_ACRO_COM = 0, 1, 2, 3, 4
 
 OPT_GENERAL_KERNELS = 1
+OPT_SPECIALIZE = 2
 CELL_FROZEN, CELL_HOLE, CELL_GOAL, CELL_START = 0, 1, 2, 3
 STAT_KEYS = ("steps", "episodes", "return_sum", "length_sum", "terminated", "truncated", "rejected_updates",
              "bad_dist")
@@ -104,7 +105,7 @@ EXPORTS = [
     "nsgym_abi_version", "nsgym_sizeof", "nsgym_last_error", "nsgym_create", "nsgym_create_rows", "nsgym_destroy",
     "nsgym_layout", "nsgym_bind", "nsgym_reset", "nsgym_step", "nsgym_step_many", "nsgym_unpack", "nsgym_episode_stats", "nsgym_step_host", "nsgym_alloc_host", "nsgym_free_host",
     "nsgym_rollout", "nsgym_rollout_linear", "nsgym_fanout", "nsgym_snapshot_bytes", "nsgym_snapshot", "nsgym_restore", "nsgym_transition_table", "nsgym_set_option", "nsgym_eval_update", "nsgym_eval_w1", "nsgym_eval_draws", "nsgym_set_seed", "nsgym_step_index", "nsgym_set_step_index",
-    "nsgym_launch_count", "nsgym_last_kernel_class",
+    "nsgym_launch_count", "nsgym_last_kernel_class", "nsgym_last_kernel_specialized", "nsgym_jit_check", "nsgym_jit_stats",
 ]
 
 _lib = None
@@ -190,6 +191,9 @@ def load(build_if_missing: bool = False):
     lib.nsgym_launch_count.restype = C.c_int64
     lib.nsgym_launch_count.argtypes = [C.c_void_p]
     lib.nsgym_last_kernel_class.argtypes = [C.c_void_p]
+    lib.nsgym_last_kernel_specialized.argtypes = [C.c_void_p]
+    lib.nsgym_jit_check.argtypes = [C.POINTER(NsgymSpec), C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.nsgym_jit_stats.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
     if lib.nsgym_abi_version() != ABI_VERSION:
         raise NsgymError("libnsgym_b200.so ABI version differs from ns_gym_b200/native.py")
     for which, st in enumerate((NsgymSlot, NsgymSpec, NsgymLayout, NsgymBuffers, NsgymHostOut, NsgymSnapshotInfo)):

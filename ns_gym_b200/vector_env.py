@@ -530,9 +530,16 @@ class NSVectorEnv:
 
     def set_option(self, name: str, value) -> None:
         """Handle options (``nsgym_set_option``): ``"general_kernels"`` forces the general kernel
-        instantiations instead of the lean ones picked for this program (same results)."""
-        opt = {"general_kernels": nv.OPT_GENERAL_KERNELS}[name]
+        instantiations instead of the lean ones picked for this program (same results);
+        ``"specialize"`` (-1 auto / 0 / 1) runs a lean program through a step kernel compiled at run
+        time for exactly this program (NVRTC; auto = batches of >= 32768 envs)."""
+        opt = {"general_kernels": nv.OPT_GENERAL_KERNELS, "specialize": nv.OPT_SPECIALIZE}[name]
         nv.check(self.lib.nsgym_set_option(self._h, opt, int(value)), "nsgym_set_option")
+
+    @property
+    def last_kernel_specialized(self) -> bool:
+        """Did the last step / rollout launch run a program-specialised kernel?"""
+        return bool(self.lib.nsgym_last_kernel_specialized(self._h))
 
     def snapshot(self):
         """Device copy of everything a step mutates; ``restore`` rewinds the batch to it."""

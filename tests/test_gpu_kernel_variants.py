@@ -19,13 +19,14 @@ CASES_UNDER_TEST = ["c1_cartpole_readme", "cartpole_silent", "cartpole_persisten
                     "c4_cartpole_rows", "c4_frozenlake8_rows"]
 
 
-def _run(case, precision, general, n=4096, steps=40, seed=9):
+def _run(case, precision, general, n=4096, steps=40, seed=9, specialize=0, info=None, **env_kw):
     import torch
 
     from tests import parity_util as pu
 
-    env = pu.gpu_env(case, n, precision=precision)
+    env = pu.gpu_env(case, n, precision=precision, **env_kw)
     env.set_option("general_kernels", general)
+    env.set_option("specialize", specialize)     # off unless a test asks: the precompiled kernels are under test
     env.reset(seed=seed)
     g = torch.Generator(device=env.device)
     g.manual_seed(1)
@@ -36,6 +37,9 @@ def _run(case, precision, general, n=4096, steps=40, seed=9):
         else:
             a = torch.randint(0, env.action_space_n, (n,), generator=g, device=env.device, dtype=torch.int32)
         env.step_raw(a)
+        if info is not None:
+            info.setdefault("specialized", []).append(env.last_kernel_specialized)
+            info.setdefault("class", []).append(int(env.lib.nsgym_last_kernel_class(env._h)))
         out.append({k2: v.clone() for k2, v in env.buffers.items() if v is not None and k2 != "action"})
     return out
 
@@ -83,3 +87,73 @@ def test_lean_kernels_track_general_kernels_fp32(name):
             if key in lean[k]:
                 np.testing.assert_allclose(lean[k][key].cpu().numpy(), general[k][key].cpu().numpy(),
                                            rtol=2e-4, atol=2e-5, err_msg=f"{name}: {key} step {k}")
+
+
+# ---- program-specialised kernels (nsgym_jit.cu): the same device code compiled at run time with the
+# ---- program as a compile-time constant, against the precompiled lean kernels on the same native draws
+SPECIALISING = ["c1_cartpole_readme", "cartpole_silent", "cartpole_persistent", "c3_acrobot", "c3_mountaincar",
+                "c3_pendulum", "mountaincar_continuous", "mountaincar_constraint", "acrobot_constraints"]
+
+
+def _assert_specialised_where_lean(name, info):
+    """Programs of the lean kernel classes run the specialised kernel; a program with a slow-class slot
+    (cartpole_persistent: CyclicUpdate) keeps the general kernel."""
+    from ns_gym_b200 import native as nv
+
+    lean = [c in (nv.KERNEL_LEAN_FAST, nv.KERNEL_LEAN_MEDIUM) for c in info["class"]]
+    assert info["specialized"] == lean, f"{name}: specialised {info['specialized'][:3]} vs lean class {lean[:3]}"
+    if name != "cartpole_persistent":
+        assert all(lean), f"{name}: expected a lean program"
+
+
+@pytest.mark.parametrize("buffers", [dict(), dict(want_delta=False, want_obs=False)])
+@pytest.mark.parametrize("name", SPECIALISING)
+def test_specialised_kernels_equal_precompiled_kernels_fp64(name, buffers):
+    import torch
+
+    case = CASES[name]
+    info = {}
+    spec = _run(case, "fp64", False, specialize=1, info=info, **buffers)
+    lean = _run(case, "fp64", False, specialize=0, **buffers)
+    _assert_specialised_where_lean(name, info)
+    for k, (x, y) in enumerate(zip(spec, lean)):
+        for key in x:
+            assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+
+
+@pytest.mark.parametrize("name", SPECIALISING)
+def test_specialised_kernels_track_precompiled_kernels_fp32(name):
+    """fp32: folded constants may change an FMA contraction, so the two kernels agree to rounding over the
+    first steps; the integer outputs of step 0 are identical."""
+    import torch
+
+    case = CASES[name]
+    info = {}
+    spec = _run(case, "fp32", False, steps=6, specialize=1, info=info)
+    lean = _run(case, "fp32", False, steps=6, specialize=0)
+    _assert_specialised_where_lean(name, info)
+    for key in ("flags", "change", "t"):
+        assert torch.equal(spec[0][key], lean[0][key])
+    for k in range(6):
+        for key in ("state", "theta", "reward", "obs", "delta"):
+            if key in spec[k]:
+                np.testing.assert_allclose(spec[k][key].cpu().numpy(), lean[k][key].cpu().numpy(),
+                                           rtol=2e-4, atol=2e-5, err_msg=f"{name}: {key} step {k}")
+
+
+def test_specialisation_is_automatic_for_large_batches_only():
+    import torch
+
+    from tests import parity_util as pu
+
+    for n, want in ((4096, False), (32768, True)):
+        env = pu.gpu_env(CASES["c1_cartpole_readme"], n, precision="fp32")
+        env.reset(seed=1)
+        env.step_raw(torch.zeros(n, dtype=torch.int32, device=env.device))
+        assert env.last_kernel_specialized == want
+    # general kernels (injection, slow rule classes) never specialise
+    env = pu.gpu_env(CASES["c1_cartpole_readme"], 32768, precision="fp32")
+    env.set_option("general_kernels", 1)
+    env.reset(seed=1)
+    env.step_raw(torch.zeros(32768, dtype=torch.int32, device=env.device))
+    assert not env.last_kernel_specialized

@@ -1,0 +1,55 @@
+"""CPU: the program specialiser (nsgym_jit.cu) generates and compiles -- NVRTC, no device needed -- the
+step kernel of every case program that stays in the lean kernel classes, in both precisions."""
+import ctypes as C
+
+import pytest
+
+import ns_gym_b200.schedulers as S
+import ns_gym_b200.update_functions as U
+from ns_gym_b200 import native as nv
+from ns_gym_b200.compile import compile_program
+from tests.cases import CASES
+
+CLASSIC = sorted(n for n, c in CASES.items()
+                 if "params" in c and c["env_id"].split("-")[0] in
+                 ("CartPole", "Acrobot", "MountainCar", "MountainCarContinuous", "Pendulum"))
+
+
+def _check(spec, want_delta, want_obs):
+    lib = nv.load()
+    src = C.create_string_buffer(1 << 16)
+    log = C.create_string_buffer(1 << 14)
+    rc = lib.nsgym_jit_check(C.byref(spec), want_delta, want_obs, src, len(src), log, len(log))
+    return rc, src.value.decode(), log.value.decode(), (lib.nsgym_last_error() or b"").decode()
+
+
+def test_nvrtc_is_available():
+    p = compile_program("CartPole-v1", {"masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)}, 16)
+    rc, src, log, err = _check(p.spec, 0, 0)
+    assert rc > 0, (rc, err, log)
+    assert "classic_step_body<float, 0, 1, 0, nsg::SpecFix>" in src
+    assert "prefetch = 0, want_delta = 0, has_obs = 0, root = 1" in src
+
+
+@pytest.mark.parametrize("precision", ["fp32", "fp64"])
+@pytest.mark.parametrize("name", CLASSIC)
+def test_every_lean_classic_case_specialises(name, precision):
+    c = CASES[name]
+    p = compile_program(c["env_id"], c["params"](S, U), 16, precision=precision, **c["wrapper"], **c["make"])
+    rc, src, log, err = _check(p.spec, 1, 1)
+    if rc == -2:        # slow rule classes: no specialised kernel, by design
+        assert "does not specialise" in err
+        return
+    assert rc > 0, (name, rc, err, log)
+    real = "float" if precision == "fp32" else "double"
+    assert f"nsg::StepIO<{real}>" in src and "want_delta = 1" in src
+
+
+def test_distinct_programs_give_distinct_sources():
+    a = compile_program("CartPole-v1", {"masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)}, 16)
+    b = compile_program("CartPole-v1", {"masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.2)}, 16)
+    sa, sb = _check(a.spec, 0, 0)[1], _check(b.spec, 0, 0)[1]
+    assert sa and sb and sa != sb
+    # the batch size and the seed are launch arguments, not part of the program
+    c = compile_program("CartPole-v1", {"masspole": U.IncrementUpdate(S.ContinuousScheduler(), k=0.1)}, 4096, seed=7)
+    assert _check(c.spec, 0, 0)[1] == sa
