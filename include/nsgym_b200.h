@@ -391,12 +391,13 @@ enum { NSGYM_OPT_GENERAL_KERNELS = 1, NSGYM_OPT_SPECIALIZE = 2 };
 int nsgym_set_option(NsgymHandle* h, int option, int64_t value);
 /* 1 when the handle's last step / rollout launch went to a program-specialised kernel */
 int nsgym_last_kernel_specialized(const NsgymHandle* h);
-/* Generate and compile (no device needed) the specialised step kernel of `spec` as a handle with / without
- * delta and float32-observation buffers would run it; copies the source and the compiler log out when
- * asked.  Returns the cubin size, -2 when the program does not specialise, -3 when NVRTC is missing or the
+/* Generate and compile (no device needed) the specialised single-step (rollout = 0) or fused-rollout
+ * (rollout = 1, uniform-random policy) kernel of `spec` as a handle with / without delta and
+ * float32-observation buffers would run it; copies the source and the compiler log out when asked.
+ * Returns the cubin size, -2 when the program does not specialise, -3 when NVRTC is missing or the
  * compilation fails (nsgym_last_error says which). */
-int nsgym_jit_check(const NsgymSpec* spec, int want_delta, int want_obs, char* source, size_t source_len, char* log,
-                    size_t log_len);
+int nsgym_jit_check(const NsgymSpec* spec, int rollout, int want_delta, int want_obs, char* source, size_t source_len,
+                    char* log, size_t log_len);
 /* process-wide counters of the specialiser; returns 1 when it is enabled */
 int nsgym_jit_stats(int64_t* compiled, int64_t* hits, int64_t* failed, char* last_failure, size_t len);
 

@@ -836,8 +836,8 @@ int64_t nsgym_launch_count(const NsgymHandle* h) { return h ? h->launches : 0; }
 int nsgym_last_kernel_class(const NsgymHandle* h) { return h ? h->kernel_class : -1; }
 int nsgym_last_kernel_specialized(const NsgymHandle* h) { return h ? h->specialized : 0; }
 
-int nsgym_jit_check(const NsgymSpec* spec, int want_delta, int want_obs, char* source, size_t source_len, char* log,
-                    size_t log_len) {
+int nsgym_jit_check(const NsgymSpec* spec, int rollout, int want_delta, int want_obs, char* source, size_t source_len,
+                    char* log, size_t log_len) {
   if (int rc = validate(spec)) return rc;
   NsgymSpec s = *spec;   // as nsgym_create keeps it (no device needed up to here)
   for (int j = 0; j < s.n_slots; ++j) nsg::set_mod_magic(&s.slots[j], *spec);
@@ -853,10 +853,13 @@ int nsgym_jit_check(const NsgymSpec* spec, int want_delta, int want_obs, char* s
   std::string src;
   io.spec_source = &src;
   const nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr};
+  const nsg::LaunchOp op = rollout ? nsg::OP_ROLLOUT : nsg::OP_STEP;
+  io.k_steps = 1;
+  io.gamma = 1.f;
   cudaError_t e;
-  if (nsg::is_grid_kind(s.env_kind)) return fail(-2, "gridworld programs do not specialise yet");
-  if (s.precision == NSGYM_F64) e = nsg::launch_classic_f64(nsg::OP_STEP, s, pools, io, nullptr);
-  else e = nsg::launch_classic_f32(nsg::OP_STEP, s, pools, io, nullptr);
+  if (nsg::is_grid_kind(s.env_kind)) e = nsg::launch_grid(op, s, pools, io, nullptr);
+  else if (s.precision == NSGYM_F64) e = nsg::launch_classic_f64(op, s, pools, io, nullptr);
+  else e = nsg::launch_classic_f32(op, s, pools, io, nullptr);
   if (e != cudaSuccess || src.empty()) return fail(-2, "this program does not specialise (general kernel class or per-env rows)");
   if (source && source_len) { std::strncpy(source, src.c_str(), source_len - 1); source[source_len - 1] = 0; }
   std::vector<char> cubin;

@@ -207,27 +207,61 @@ static StepIO<R> build_io(const LaunchIO& a) {
   return io;
 }
 
-// Source of the program-specialised single-step kernel of a lean program (nsgym_jit.cu): the body the
-// precompiled kernel runs (classic_step_body), with the lowered program rebuilt as a constexpr object
-// from the words of the host's ProgramHeadT and the launch facts fixed in SpecFix.
+// ---- sources of the program-specialised kernels (nsgym_jit.cu) ----
+// `dst = the host object's words`, for a pointer-free object of type `type`
+template <typename T>
+static std::string spec_assign(const std::string& dst, const std::string& type, const T& obj) {
+  static_assert(sizeof(T) % 4 == 0, "a whole number of words");
+  return "  " + dst + " = __builtin_bit_cast(" + type + ", SpecWords<" + std::to_string(sizeof(T) / 4) + ">{{" +
+         jit::words(&obj, sizeof(T)) + "}});\n";
+}
+// launch facts fixed at compile time (device side: NoFix / SpecFix)
+template <typename R>
+static std::string spec_prelude(const char* header, const StepIO<R>& io, bool root) {
+  return std::string("#include \"") + header + "\"\nnamespace nsg {\ntemplate <int N> struct SpecWords { uint32_t w[N]; };\n" +
+         "struct SpecFix { static constexpr int prefetch = " + std::to_string(io.prefetch ? 1 : 0) +
+         ", want_delta = " + std::to_string(io.delta ? 1 : 0) + ", has_obs = " + std::to_string(io.obs ? 1 : 0) +
+         ", root = " + std::to_string(root ? 1 : -1) + "; };\n";
+}
+template <typename R>
+static uint32_t spec_facts(const StepIO<R>& io, bool root) {
+  return (io.prefetch ? 4u : 0u) | (io.delta ? 8u : 0u) | (io.obs ? 16u : 0u) | (root ? 32u : 0u);
+}
+
+// The single-step kernel of a lean classic-control program: the body the precompiled kernel runs
+// (classic_step_body), with the lowered program rebuilt as a constexpr object from the words of the
+// host's ProgramHeadT and the launch facts fixed in SpecFix.
 template <typename R, int KIND, int NP>
 static std::string spec_step_source(const ProgramT<R, NP>& P, int level, const StepIO<R>& io, bool root) {
-  const char* real = std::is_same<R, float>::value ? "float" : "double";
+  const std::string real = std::is_same<R, float>::value ? "float" : "double";
   const ProgramHeadT<R, NP>& head = P;
-  static_assert(sizeof(ProgramHeadT<R, NP>) % 4 == 0, "program head is a whole number of words");
-  const std::string prog = std::string("ProgramT<") + real + ", " + std::to_string(NP) + ">";
-  const std::string headt = std::string("ProgramHeadT<") + real + ", " + std::to_string(NP) + ">";
-  std::string s = "#include \"nsgym_device.cuh\"\nnamespace nsg {\ntemplate <int N> struct SpecWords { uint32_t w[N]; };\n";
-  s += "struct SpecFix { static constexpr int prefetch = " + std::to_string(io.prefetch ? 1 : 0) +
-       ", want_delta = " + std::to_string(io.delta ? 1 : 0) + ", has_obs = " + std::to_string(io.obs ? 1 : 0) +
-       ", root = " + std::to_string(root ? 1 : -1) + "; };\n";
-  s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n  static_cast<" + headt +
-       "&>(P) = __builtin_bit_cast(" + headt + ", SpecWords<" + std::to_string(sizeof(head) / 4) + ">{{" +
-       jit::words(&head, sizeof(head)) + "}});\n  return P;\n}\n}  // namespace nsg\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::classic_min_blocks<" + std::string(real) + ", " +
+  const std::string prog = "ProgramT<" + real + ", " + std::to_string(NP) + ">";
+  const std::string headt = "ProgramHeadT<" + real + ", " + std::to_string(NP) + ">";
+  std::string s = spec_prelude<R>("nsgym_device.cuh", io, root);
+  s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
+       spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::classic_spec_min_blocks<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(level) + ">())\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<" +
        real + "> io) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n  nsg::classic_step_body<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", nsg::SpecFix>(P, io);\n}\n";
+  return s;
+}
+
+// K fused steps of a lean classic-control program (classic_rollout_body); `lin`: linear rollout policy
+template <typename R, int KIND, int NP>
+static std::string spec_rollout_source(const ProgramT<R, NP>& P, int level, const StepIO<R>& io, bool root, bool lin) {
+  const std::string real = std::is_same<R, float>::value ? "float" : "double";
+  const ProgramHeadT<R, NP>& head = P;
+  const std::string prog = "ProgramT<" + real + ", " + std::to_string(NP) + ">";
+  const std::string headt = "ProgramHeadT<" + real + ", " + std::to_string(NP) + ">";
+  std::string s = spec_prelude<R>("nsgym_device.cuh", io, root);
+  s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
+       spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
+  s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<" + real +
+       "> io, const __grid_constant__ nsg::RolloutArgs ra) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n"
+       "  const nsg::HetT<" + real + ", " + std::to_string(NP) + "> no_rows{};\n  nsg::classic_rollout_body<" + real + ", " +
+       std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", false, " + (lin ? "true" : "false") +
+       ", nsg::SpecFix>(P, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, static_cast<const float*>(ra.pol), ra.pol_per_env);\n}\n";
   return s;
 }
 
@@ -242,6 +276,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   const unsigned grid = unsigned((a.count + block - 1) / block);
   if (grid == 0) return cudaSuccess;
   if (a.rows && a.rows->active) {       // heterogeneous handle: per-env rows
+    if (a.spec_source) return cudaErrorNotSupported;
     if constexpr (NP == 0) return cudaErrorInvalidValue;
     else {
       const HetT<R, NP> H = build_het<R, NP>(*a.rows);
@@ -277,8 +312,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   if (op == OP_STEP && level < 2 && (a.specialize || a.spec_source)) {
     // lean program: the kernel compiled for exactly this program (cached per distinct source)
     const bool root = a.plan_elapsed < 0 && !a.skip_updates;
-    const uint32_t facts = uint32_t(level) | (io.prefetch ? 4u : 0u) | (io.delta ? 8u : 0u) | (io.obs ? 16u : 0u) |
-                           (root ? 32u : 0u);
+    const uint32_t facts = uint32_t(level) | spec_facts(io, root);
     cudaKernel_t k = nullptr;
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
       const std::string src = spec_step_source<R, KIND, NP>(P, level, io, root);
@@ -292,6 +326,25 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(lean_grid), dim3(block), args, 0, stream);
     }
   }
+  if (op == OP_ROLLOUT && level < 2 && NP > 0 && (a.specialize || a.spec_source)) {
+    const bool root = a.plan_elapsed < 0 && !a.skip_updates;
+    const bool lin = a.policy != nullptr;
+    const uint32_t facts = uint32_t(level) | spec_facts(io, root) | 64u | (lin ? 128u : 0u);
+    cudaKernel_t k = nullptr;
+    if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
+      const std::string src = spec_rollout_source<R, KIND, NP>(P, level, io, root, lin);
+      if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
+      k = jit::kernel(src, std::is_same<R, float>::value, nullptr);
+      if (a.spec_cache) a.spec_cache->put(facts, k);
+    }
+    if (k) {
+      RolloutArgs ra{a.k_steps, a.gamma, a.ret, a.len, a.policy, a.policy_per_env};
+      void* args[] = {const_cast<StepIO<R>*>(&io), &ra};
+      if (a.specialized) *a.specialized = 1;
+      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
+    }
+  }
+  if (a.spec_source) return cudaErrorNotSupported;   // nsgym_jit_check on a program of the general class: nothing to generate
   switch (op) {
     case OP_STEP:
       if (level == 2) classic_step_kernel<R, KIND, NP, 2><<<grid, block, 0, stream>>>(P, io);

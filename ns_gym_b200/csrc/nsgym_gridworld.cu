@@ -2,6 +2,7 @@
 // this unit is built with -fmad=false: cumulative sums and W1 distances match NumPy exactly.
 #include <cstdio>
 #include <cstring>
+#include <string>
 
 #include "nsgym_grid.cuh"
 #include "nsgym_classic_launch.cuh"
@@ -42,6 +43,48 @@ static HetT<double, MAXP> build_het_by_index(const NsgymSpec& spec, const RowTab
   return H;
 }
 
+// the pointer-free parts of a GridProgram as a constexpr function of the specialised sources
+template <int MAXP>
+static std::string spec_grid_program_source(const GridProgram<MAXP>& G) {
+  const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
+  const std::string headt = "ProgramHeadT<double, " + std::to_string(MAXP) + ">";
+  const GridConsts& consts = G;
+  const ProgramHeadT<double, MAXP>& head = G.base;
+  return "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " G{};\n" +
+         spec_assign("static_cast<GridConsts&>(G)", "GridConsts", consts) +
+         spec_assign("static_cast<" + headt + "&>(G.base)", headt, head) + "  return G;\n}\n}  // namespace nsg\n";
+}
+
+// The single-step kernel of a lean gridworld program (deterministic schedulers and rules): grid_step_body
+// with everything but the four device pointers of the program as a compile-time constant.
+template <int KIND, int D, int MAXP>
+static std::string spec_grid_step_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root) {
+  const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
+  std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
+  s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::grid_spec_min_blocks<" + std::to_string(KIND) +
+       ">())\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs) {\n"
+       "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
+       "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
+       "  nsg::grid_step_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
+       ", false, nsg::SpecFix>(G, io);\n}\n";
+  return s;
+}
+
+// K fused steps of a lean gridworld program under the uniform-random policy (grid_rollout_body)
+template <int KIND, int D, int MAXP>
+static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root) {
+  const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
+  std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
+  s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<double> io, "
+       "const __grid_constant__ nsg::GridPtrs ptrs, const __grid_constant__ nsg::RolloutArgs ra) {\n"
+       "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
+       "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
+       "  const nsg::HetT<double, " + std::to_string(MAXP) + "> no_rows{};\n"
+       "  nsg::grid_rollout_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
+       ", false, false, false, nsg::SpecFix>(G, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, nullptr, 0);\n}\n";
+  return s;
+}
+
 template <int KIND, int D, int MAXP>
 static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const DevicePools& pools, const LaunchIO& a,
                                  cudaStream_t stream) {
@@ -66,6 +109,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     else *a.kernel_class = slow ? NSGYM_KERNEL_GENERAL : NSGYM_KERNEL_LEAN_FAST;
   }
   if (het) {
+    if (a.spec_source) return cudaErrorNotSupported;
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     switch (op) {
       case OP_STEP:
@@ -85,6 +129,43 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     return cudaGetLastError();
   }
   const HetT<double, MAXP> no_rows{};
+  if (a.specialized) *a.specialized = 0;
+  if (op == OP_STEP && !slow && (a.specialize || a.spec_source)) {
+    const bool root = a.plan_elapsed < 0 && !a.skip_updates;
+    const uint32_t facts = spec_facts(io, root);
+    cudaKernel_t k = nullptr;
+    if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
+      const std::string src = spec_grid_step_source<KIND, D, MAXP>(G, io, root);
+      if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
+      k = jit::kernel(src, false, nullptr);
+      if (a.spec_cache) a.spec_cache->put(facts, k);
+    }
+    if (k) {
+      GridPtrs ptrs{G.base.pool_f, G.base.pool_i, G.base.bitmap, G.tab};
+      void* args[] = {const_cast<StepIO<double>*>(&io), &ptrs};
+      if (a.specialized) *a.specialized = 1;
+      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
+    }
+  }
+  if (op == OP_ROLLOUT && !slow && !a.policy && (a.specialize || a.spec_source)) {
+    const bool root = a.plan_elapsed < 0 && !a.skip_updates;
+    const uint32_t facts = spec_facts(io, root) | 64u;
+    cudaKernel_t k = nullptr;
+    if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
+      const std::string src = spec_grid_rollout_source<KIND, D, MAXP>(G, io, root);
+      if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
+      k = jit::kernel(src, false, nullptr);
+      if (a.spec_cache) a.spec_cache->put(facts, k);
+    }
+    if (k) {
+      GridPtrs ptrs{G.base.pool_f, G.base.pool_i, G.base.bitmap, G.tab};
+      RolloutArgs ra{a.k_steps, a.gamma, a.ret, a.len, nullptr, 0};
+      void* args[] = {const_cast<StepIO<double>*>(&io), &ptrs, &ra};
+      if (a.specialized) *a.specialized = 1;
+      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
+    }
+  }
+  if (a.spec_source) return cudaErrorNotSupported;
   switch (op) {
     case OP_STEP:
       if (slow) grid_step_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, io);

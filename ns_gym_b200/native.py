@@ -192,7 +192,7 @@ def load(build_if_missing: bool = False):
     lib.nsgym_launch_count.argtypes = [C.c_void_p]
     lib.nsgym_last_kernel_class.argtypes = [C.c_void_p]
     lib.nsgym_last_kernel_specialized.argtypes = [C.c_void_p]
-    lib.nsgym_jit_check.argtypes = [C.POINTER(NsgymSpec), C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
+    lib.nsgym_jit_check.argtypes = [C.POINTER(NsgymSpec), C.c_int, C.c_int, C.c_int, C.c_char_p, C.c_size_t, C.c_char_p, C.c_size_t]
     lib.nsgym_jit_stats.argtypes = [C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.POINTER(C.c_int64), C.c_char_p, C.c_size_t]
     if lib.nsgym_abi_version() != ABI_VERSION:
         raise NsgymError("libnsgym_b200.so ABI version differs from ns_gym_b200/native.py")

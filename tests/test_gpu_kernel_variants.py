@@ -93,6 +93,8 @@ def test_lean_kernels_track_general_kernels_fp32(name):
 # ---- program as a compile-time constant, against the precompiled lean kernels on the same native draws
 SPECIALISING = ["c1_cartpole_readme", "cartpole_silent", "cartpole_persistent", "c3_acrobot", "c3_mountaincar",
                 "c3_pendulum", "mountaincar_continuous", "mountaincar_constraint", "acrobot_constraints"]
+SPECIALISING_GRID = ["c2_frozenlake8_drift", "c2_frozenlake8_stepchange", "frozenlake8_lerp", "frozenlake8_cyclic_stale",
+                     "cliff_terminal", "cliff_drift", "c5_bridge_uniform", "c5_bridge_split", "bridge_stepwise"]
 
 
 def _assert_specialised_where_lean(name, info):
@@ -106,8 +108,23 @@ def _assert_specialised_where_lean(name, info):
         assert all(lean), f"{name}: expected a lean program"
 
 
+@pytest.mark.parametrize("name", ["frozenlake8_cyclic_stale", "bridge_stepwise", "c5_bridge_uniform"])
+def test_specialised_gridworld_kernels_with_persistent_params_fp64(name):
+    import torch
+
+    case = dict(CASES[name])
+    case["wrapper"] = dict(case.get("wrapper", {}), persistent_params=True)
+    info = {}
+    spec = _run(case, "fp64", False, steps=60, specialize=1, info=info)
+    general = _run(case, "fp64", True, steps=60)
+    assert all(info["specialized"])
+    for k, (x, y) in enumerate(zip(spec, general)):
+        for key in x:
+            assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+
+
 @pytest.mark.parametrize("buffers", [dict(), dict(want_delta=False, want_obs=False)])
-@pytest.mark.parametrize("name", SPECIALISING)
+@pytest.mark.parametrize("name", SPECIALISING + SPECIALISING_GRID)
 def test_specialised_kernels_equal_precompiled_kernels_fp64(name, buffers):
     import torch
 

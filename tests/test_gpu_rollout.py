@@ -19,27 +19,32 @@ ROLLOUT_CASES = [("c1_cartpole_readme", "cartpole", "fp32"), ("c1_cartpole_readm
                  ("cliff_terminal", "grid", "fp64")]
 
 
-def _make(case, n, precision, seed, offset=0):
+def _make(case, n, precision, seed, offset=0, specialize=0):
     import ns_gym_b200.schedulers as PS
     import ns_gym_b200.update_functions as PU
     from ns_gym_b200.vector_env import NSVectorEnv
 
     env = NSVectorEnv(case["env_id"], case["params"](PS, PU), n, precision=precision, seed=seed,
                       env_id_offset=offset, **case.get("wrapper", {}), **case.get("make", {}))
+    env.set_option("specialize", specialize)
     env.reset(seed=seed)
     return env
 
 
+# specialize = 1: the program-specialised rollout kernel (nsgym_jit.cu) against the program-specialised
+# single-step kernel -- the same device functions, compiled with the program as a constant
+@pytest.mark.parametrize("specialize", [0, 1])
 @pytest.mark.parametrize("name,kind,precision", ROLLOUT_CASES)
-def test_rollout_equals_single_steps(name, kind, precision):
+def test_rollout_equals_single_steps(name, kind, precision, specialize):
     import torch
 
     case, n, K, seed, offset = CASES[name], 4096, 37, 1234, 10_000
-    a = _make(case, n, precision, seed, offset)
-    b = _make(case, n, precision, seed, offset)
+    a = _make(case, n, precision, seed, offset, specialize)
+    b = _make(case, n, precision, seed, offset, specialize)
     step0 = int(a.lib.nsgym_step_index(a._h))
     assert step0 == int(b.lib.nsgym_step_index(b._h))
     ret, length = a.rollout(K, gamma=1.0)
+    assert a.last_kernel_specialized == bool(specialize)
     gids = np.arange(offset, offset + n, dtype=np.uint64)
     acc = torch.zeros(n, dtype=torch.float32, device=b.device)
     steps_alive = torch.zeros(n, dtype=torch.int32, device=b.device)
@@ -47,6 +52,7 @@ def test_rollout_equals_single_steps(name, kind, precision):
     for k in range(K):
         act = philox_np.policy_actions(kind, gids, step0 + k, seed, precision)
         obs, r, term, trunc, info = b.step(torch.as_tensor(act))
+        assert b.last_kernel_specialized == bool(specialize)
         was_reset = info["was_reset"]
         first &= ~was_reset
         steps_alive += (first & ~was_reset).int()

@@ -13,13 +13,14 @@ from tests.cases import CASES
 CLASSIC = sorted(n for n, c in CASES.items()
                  if "params" in c and c["env_id"].split("-")[0] in
                  ("CartPole", "Acrobot", "MountainCar", "MountainCarContinuous", "Pendulum"))
+GRID = sorted(n for n, c in CASES.items() if "params" in c and n not in CLASSIC)
 
 
-def _check(spec, want_delta, want_obs):
+def _check(spec, want_delta, want_obs, rollout=0):
     lib = nv.load()
     src = C.create_string_buffer(1 << 16)
     log = C.create_string_buffer(1 << 14)
-    rc = lib.nsgym_jit_check(C.byref(spec), want_delta, want_obs, src, len(src), log, len(log))
+    rc = lib.nsgym_jit_check(C.byref(spec), rollout, want_delta, want_obs, src, len(src), log, len(log))
     return rc, src.value.decode(), log.value.decode(), (lib.nsgym_last_error() or b"").decode()
 
 
@@ -43,6 +44,22 @@ def test_every_lean_classic_case_specialises(name, precision):
     assert rc > 0, (name, rc, err, log)
     real = "float" if precision == "fp32" else "double"
     assert f"nsg::StepIO<{real}>" in src and "want_delta = 1" in src
+    if len(c["params"](S, U)):     # the fused rollout of the same program
+        rc, src, log, err = _check(p.spec, 0, 1, rollout=1)
+        assert rc > 0 and "classic_rollout_body<" in src, (name, rc, err, log)
+
+
+@pytest.mark.parametrize("name", GRID)
+def test_every_lean_gridworld_case_specialises(name):
+    c = CASES[name]
+    p = compile_program(c["env_id"], c["params"](S, U), 16, precision="fp64", **c["wrapper"], **c["make"])
+    rc, src, log, err = _check(p.spec, 1, 0)
+    if rc == -2:        # stochastic scheduler / RandomCategorical / Lipschitz-bounded rule: general kernel
+        return
+    assert rc > 0, (name, rc, err, log)
+    assert "grid_step_body<" in src and "GridPtrs ptrs" in src
+    rc, src, log, err = _check(p.spec, 0, 0, rollout=1)
+    assert rc > 0 and "grid_rollout_body<" in src, (name, rc, err, log)
 
 
 def test_distinct_programs_give_distinct_sources():
