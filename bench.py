@@ -648,6 +648,7 @@ def run_gpu(args):
     if dist is not None:
         dist.all_reduce(cvec, op=dist.ReduceOp.SUM)
     # ---- metric reduction over NCCL (the only collective on this path) ----
+    specialised = all(getattr(s, "last_kernel_specialized", False) for s in shards)
     stats = torch.stack([sum(s.buffers["reward"].double().sum() for s in shards),
                          sum(((s.buffers["flags"] & 3) != 0).double().sum() for s in shards),
                          torch.tensor(float(n_envs), dtype=torch.float64, device=dev)])
@@ -685,7 +686,7 @@ def run_gpu(args):
                 "autoreset": "next_step", "rng": "philox4x32-10 (native)", "rollout_k": rollout_k, "rollout_policy": args.rollout_policy if rollout_k else None,
                 "kernels": "general" if args.general_kernels else (
                     "program-specialised (NVRTC at first launch, nsgym_jit.cu)"
-                    if all(getattr(s, "last_kernel_specialized", False) for s in shards)
+                    if specialised
                     else "precompiled lean where the program allows"),
                 "parallelism": f"env-shard x{world}, no data-path collective",
                 "l2_policy": f"working set {bytes_per_launch_env * n_envs / 1e6:.0f} MB per GPU >> 126 MB L2 "

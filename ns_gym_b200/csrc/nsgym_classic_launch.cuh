@@ -241,9 +241,46 @@ static std::string spec_step_source(const ProgramT<R, NP>& P, int level, const S
   s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
        spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
   s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::classic_spec_min_blocks<" + real + ", " +
-       std::to_string(KIND) + ", " + std::to_string(level) + ">())\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<" +
+       std::to_string(KIND) + ", " + std::to_string(level) + ">())\nnsgym_spec_classic_step(const __grid_constant__ nsg::StepIO<" +
        real + "> io) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n  nsg::classic_step_body<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", nsg::SpecFix>(P, io);\n}\n";
+  return s;
+}
+
+// `spec_rows()`: the row layout (which words vary, their planes, the shared defaults) as a constant
+template <typename R, int NP>
+static std::string spec_rows_source(const HetT<R, NP>& H) {
+  const std::string real = std::is_same<R, float>::value ? "float" : "double";
+  const std::string headt = "HetHeadT<" + real + ", " + std::to_string(NP) + ">";
+  const HetHeadT<R, NP>& head = H;
+  return "namespace nsg {\n__device__ constexpr " + headt + " spec_rows() {\n  " + headt + " H{};\n" +
+         spec_assign("H", headt, head) + "  return H;\n}\n}  // namespace nsg\n";
+}
+// statements that rebuild a HetT named H from spec_rows() and the kernel parameter `hp` (HetPtrs)
+static std::string spec_rows_object(const std::string& real, int np) {
+  const std::string args = real + ", " + std::to_string(np);
+  return "  constexpr nsg::HetHeadT<" + args + "> HH = nsg::spec_rows();\n  nsg::HetT<" + args + "> H{};\n"
+         "  static_cast<nsg::HetHeadT<" + args + ">&>(H) = HH;\n"
+         "  H.ints = hp.ints; H.reals = static_cast<const " + real + "*>(hp.reals); H.dbls = hp.dbls;\n";
+}
+
+// The single-step kernel of a batch with lean per-env rows (classic_step_het_body): program and row layout
+// are constants, so every lane loads exactly the row words that vary and the shared ones are immediates.
+template <typename R, int KIND, int NP>
+static std::string spec_step_rows_source(const ProgramT<R, NP>& P, const HetT<R, NP>& H, const StepIO<R>& io, bool root) {
+  const std::string real = std::is_same<R, float>::value ? "float" : "double";
+  const ProgramHeadT<R, NP>& head = P;
+  const std::string prog = "ProgramT<" + real + ", " + std::to_string(NP) + ">";
+  const std::string headt = "ProgramHeadT<" + real + ", " + std::to_string(NP) + ">";
+  std::string s = spec_prelude<R>("nsgym_device.cuh", io, root);
+  s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
+       spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
+  s += spec_rows_source<R, NP>(H);
+  s += "extern \"C\" __global__ void __launch_bounds__(256, NSGYM_HET_LEAN_MIN_BLOCKS)\nnsgym_spec_classic_step_rows("
+       "const __grid_constant__ nsg::StepIO<" + real + "> io, const __grid_constant__ nsg::HetPtrs hp) {\n"
+       "  constexpr nsg::" + prog + " P = nsg::spec_program();\n" + spec_rows_object(real, NP) +
+       "  nsg::classic_step_het_body<" + real + ", " + std::to_string(KIND) + ", " + std::to_string(NP) +
+       ", true, nsg::SpecFix>(P, H, io);\n}\n";
   return s;
 }
 
@@ -257,7 +294,7 @@ static std::string spec_rollout_source(const ProgramT<R, NP>& P, int level, cons
   std::string s = spec_prelude<R>("nsgym_device.cuh", io, root);
   s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
        spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
-  s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<" + real +
+  s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_classic_rollout(const __grid_constant__ nsg::StepIO<" + real +
        "> io, const __grid_constant__ nsg::RolloutArgs ra) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n"
        "  const nsg::HetT<" + real + ", " + std::to_string(NP) + "> no_rows{};\n  nsg::classic_rollout_body<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", false, " + (lin ? "true" : "false") +
@@ -282,6 +319,23 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       const HetT<R, NP> H = build_het<R, NP>(*a.rows);
       const bool lean_rows = a.rows->lean && !a.general_kernels && !a.inj_u && !a.inj_z;
       if (a.kernel_class) *a.kernel_class = lean_rows ? NSGYM_KERNEL_ROWS_LEAN : NSGYM_KERNEL_ROWS_GENERAL;
+      if (a.specialized) *a.specialized = 0;
+      if (op == OP_STEP && lean_rows && a.specialize) {
+        const bool root = a.plan_elapsed < 0 && !a.skip_updates;
+        const uint32_t facts = spec_facts(io, root) | 256u;
+        cudaKernel_t k = nullptr;
+        if (!a.spec_cache || !a.spec_cache->find(facts, &k)) {
+          k = jit::kernel(spec_step_rows_source<R, KIND, NP>(P, H, io, root), "nsgym_spec_classic_step_rows",
+                          std::is_same<R, float>::value, nullptr);
+          if (a.spec_cache) a.spec_cache->put(facts, k);
+        }
+        if (k) {
+          HetPtrs hp{H.ints, H.reals, H.dbls};
+          void* args[] = {const_cast<StepIO<R>*>(&io), &hp};
+          if (a.specialized) *a.specialized = 1;
+          return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
+        }
+      }
       switch (op) {
         case OP_STEP:
           if (lean_rows) classic_step_het_kernel<R, KIND, NP, true><<<grid, block, 0, stream>>>(P, H, io);
@@ -317,7 +371,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
       const std::string src = spec_step_source<R, KIND, NP>(P, level, io, root);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
-      k = jit::kernel(src, std::is_same<R, float>::value, nullptr);
+      k = jit::kernel(src, "nsgym_spec_classic_step", std::is_same<R, float>::value, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);
     }
     if (k) {
@@ -334,7 +388,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
       const std::string src = spec_rollout_source<R, KIND, NP>(P, level, io, root, lin);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
-      k = jit::kernel(src, std::is_same<R, float>::value, nullptr);
+      k = jit::kernel(src, "nsgym_spec_classic_rollout", std::is_same<R, float>::value, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);
     }
     if (k) {

@@ -62,11 +62,29 @@ static std::string spec_grid_step_source(const GridProgram<MAXP>& G, const StepI
   const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
   std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
   s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::grid_spec_min_blocks<" + std::to_string(KIND) +
-       ">())\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs) {\n"
+       ">())\nnsgym_spec_grid_step(const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs) {\n"
        "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
        "  nsg::grid_step_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
        ", false, nsg::SpecFix>(G, io);\n}\n";
+  return s;
+}
+
+// single step of a gridworld batch with lean per-env rows (grid_step_het_body)
+template <int KIND, int D, int MAXP>
+static std::string spec_grid_step_rows_source(const GridProgram<MAXP>& G, const HetT<double, MAXP>& H,
+                                              const StepIO<double>& io, bool root) {
+  const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
+  std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G) +
+                  spec_rows_source<double, MAXP>(H);
+  s += "extern \"C\" __global__ void __launch_bounds__(256, NSGYM_HET_LEAN_MIN_BLOCKS)\nnsgym_spec_grid_step_rows("
+       "const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs, "
+       "const __grid_constant__ nsg::HetPtrs hp) {\n"
+       "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
+       "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n" +
+       spec_rows_object("double", MAXP) +
+       "  nsg::grid_step_het_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
+       ", true, nsg::SpecFix>(G, H, io);\n}\n";
   return s;
 }
 
@@ -75,7 +93,7 @@ template <int KIND, int D, int MAXP>
 static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root) {
   const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
   std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
-  s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_kernel(const __grid_constant__ nsg::StepIO<double> io, "
+  s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_grid_rollout(const __grid_constant__ nsg::StepIO<double> io, "
        "const __grid_constant__ nsg::GridPtrs ptrs, const __grid_constant__ nsg::RolloutArgs ra) {\n"
        "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
@@ -111,6 +129,23 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   if (het) {
     if (a.spec_source) return cudaErrorNotSupported;
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
+    if (a.specialized) *a.specialized = 0;
+    if (op == OP_STEP && a.rows->lean && !a.general_kernels && !a.inj_u && a.specialize) {
+      const bool root = a.plan_elapsed < 0 && !a.skip_updates;
+      const uint32_t facts = spec_facts(io, root) | 256u;
+      cudaKernel_t k = nullptr;
+      if (!a.spec_cache || !a.spec_cache->find(facts, &k)) {
+        k = jit::kernel(spec_grid_step_rows_source<KIND, D, MAXP>(G, H, io, root), "nsgym_spec_grid_step_rows", false, nullptr);
+        if (a.spec_cache) a.spec_cache->put(facts, k);
+      }
+      if (k) {
+        GridPtrs ptrs{G.base.pool_f, G.base.pool_i, G.base.bitmap, G.tab};
+        HetPtrs hp{H.ints, H.reals, H.dbls};
+        void* args[] = {const_cast<StepIO<double>*>(&io), &ptrs, &hp};
+        if (a.specialized) *a.specialized = 1;
+        return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
+      }
+    }
     switch (op) {
       case OP_STEP:
         if (a.rows->lean && !a.general_kernels && !a.inj_u) grid_step_het_kernel<KIND, D, MAXP, true><<<grid, block, 0, stream>>>(G, H, io);
@@ -137,7 +172,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
       const std::string src = spec_grid_step_source<KIND, D, MAXP>(G, io, root);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
-      k = jit::kernel(src, false, nullptr);
+      k = jit::kernel(src, "nsgym_spec_grid_step", false, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);
     }
     if (k) {
@@ -154,7 +189,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
       const std::string src = spec_grid_rollout_source<KIND, D, MAXP>(G, io, root);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
-      k = jit::kernel(src, false, nullptr);
+      k = jit::kernel(src, "nsgym_spec_grid_rollout", false, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);
     }
     if (k) {

@@ -82,8 +82,9 @@ bool enabled();                                           // false when NSGYM_B2
 std::string words(const void* p, size_t bytes);           // a pointer-free object as 32-bit literals "0x..u,0x..u,..."
 // compile to an sm_100a cubin (needs NVRTC, no device); 0 or a negative status with `log` filled
 int compile(const std::string& source, bool fmad, std::vector<char>* cubin, std::string* log);
-// compiled (once per distinct source in the process) and loaded kernel `nsgym_spec_kernel`, or NULL with `why`
-cudaKernel_t kernel(const std::string& source, bool fmad, std::string* why);
+// the extern "C" kernel `entry` of `source`, compiled (once per distinct source in the process) and loaded,
+// or NULL with `why`
+cudaKernel_t kernel(const std::string& source, const char* entry, bool fmad, std::string* why);
 struct Stats { int64_t compiled = 0, hits = 0, failed = 0; std::string last_failure; };
 Stats stats();
 }  // namespace jit

@@ -174,3 +174,30 @@ def test_specialisation_is_automatic_for_large_batches_only():
     env.reset(seed=1)
     env.step_raw(torch.zeros(32768, dtype=torch.int32, device=env.device))
     assert not env.last_kernel_specialized
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", ["het_cartpole_lean", "c4_cartpole_rows", "c4_frozenlake8_rows"])
+def test_specialised_row_kernels_equal_precompiled_row_kernels(name, precision):
+    """Per-env rows: the kernel specialised on the program AND the row layout (which words vary, their
+    planes, the shared defaults) against the precompiled lean per-env kernel."""
+    import torch
+
+    from ns_gym_b200 import native as nv
+
+    case = CASES[name]
+    if precision == "fp32" and "frozenlake" in name:
+        pytest.skip("gridworld probabilities are always fp64")
+    info = {}
+    spec = _run(case, precision, False, specialize=1, info=info, steps=30)
+    lean = _run(case, precision, False, specialize=0, steps=30)
+    assert all(c == nv.KERNEL_ROWS_LEAN for c in info["class"]) and all(info["specialized"])
+    for k, (x, y) in enumerate(zip(spec, lean)):
+        for key in x:
+            if precision == "fp64" or key in ("flags", "change", "t", "istate"):
+                if precision == "fp32" and k > 0:
+                    continue
+                assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+            elif k < 6:
+                np.testing.assert_allclose(x[key].cpu().numpy(), y[key].cpu().numpy(), rtol=2e-4, atol=2e-5,
+                                           err_msg=f"{name}: {key} step {k}")

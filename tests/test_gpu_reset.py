@@ -101,3 +101,47 @@ def test_seeded_resets_replay_and_differ_across_seeds():
     a.reset(seed=10); b.reset(seed=10); c.reset(seed=11)
     assert torch.equal(a.buffers["state"], b.buffers["state"])
     assert not torch.equal(a.buffers["state"], c.buffers["state"])
+
+
+def test_slot_streams_follow_the_spawn_structure_of_the_reference():
+    """NSWrapper._seed_update_fns (base.py:412-421) gives update function j the child
+    SeedSequence(seed).spawn(P)[j]: its stream depends on (seed, j) only -- not on how many other
+    parameters are bound, nor on what they are.  Here the stream of slot j is Philox block j >> 1,
+    half j & 1 under the key `seed`: binding a third parameter, or swapping the rule of another slot,
+    leaves the draws of slot j unchanged; reset(seed) replays them, reset() lets them run on
+    (base.py:391-393: the generators are transplanted, not re-seeded)."""
+    import torch
+
+    import ns_gym_b200.schedulers as S
+    import ns_gym_b200.update_functions as U
+    from ns_gym_b200.vector_env import NSVectorEnv
+
+    def run(params, seed, steps=12, second_reset=None):
+        env = NSVectorEnv("CartPole-v1", params, 512, precision="fp64", seed=0)
+        env.reset(seed=seed)
+        a = torch.zeros(512, dtype=torch.int32, device=env.device)
+        out = []
+        for k in range(steps):
+            if second_reset is not None and k == steps // 2:
+                env.reset(**second_reset)
+            env.step_raw(a)
+            out.append(env.buffers["theta"].clone())
+        return env.keys, out
+
+    rw = lambda: U.RandomWalk(S.ContinuousScheduler(), mu=0.0, sigma=0.01)  # noqa: E731
+    k2, two = run({"gravity": rw(), "masscart": rw()}, seed=5)
+    k3, three = run({"gravity": rw(), "masscart": rw(), "length": rw()}, seed=5)
+    kx, other = run({"gravity": rw(), "masscart": U.IncrementUpdate(S.ContinuousScheduler(), k=0.001)}, seed=5)
+    for k in range(12):
+        assert torch.equal(two[k][0], three[k][0]) and torch.equal(two[k][1], three[k][1])   # slots 0, 1 unchanged
+        assert torch.equal(two[k][0], other[k][0])                                             # slot 0 unchanged
+    assert not torch.equal(three[3][2], three[3][1])                                           # slot 2 has its own stream
+    # another seed: every slot's stream changes
+    _, reseeded = run({"gravity": rw(), "masscart": rw()}, seed=6)
+    assert not torch.equal(two[0][0], reseeded[0][0])
+    # reset(seed) in mid-run replays the stream from its start; reset() continues it
+    _, replay = run({"gravity": rw(), "masscart": rw()}, seed=5, second_reset=dict(seed=5))
+    _, cont = run({"gravity": rw(), "masscart": rw()}, seed=5, second_reset=dict())
+    first_draw = two[0][0] - 9.8
+    assert torch.allclose(replay[6][0] - 9.8, first_draw, rtol=0, atol=1e-12)
+    assert not torch.allclose(cont[6][0] - 9.8, first_draw, rtol=0, atol=1e-12)

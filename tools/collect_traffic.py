@@ -38,7 +38,7 @@ def main():
             result[wl] = {"error": plain.stderr[-300:]}
             continue
         log = os.path.join(out_dir, f"r2_metrics_{wl}.csv")
-        pat = "rollout_kernel" if rollout else "step_kernel|step_het_kernel"
+        pat = "rollout_kernel|nsgym_spec_.*rollout" if rollout else "step_kernel|step_het_kernel|nsgym_spec_.*step"
         subprocess.run(["ncu", "--metrics", METRICS, "--clock-control", "none", "-k", f"regex:{pat}", "-s",
                         str(skip * per_step), "-c", str(2 * per_step), "--csv", "--log-file", log] + cmd,
                        cwd=ROOT, capture_output=True, text=True)

@@ -11,7 +11,7 @@ for wl in $wls; do
     python bench.py --workload $wl --no-specialize --no-cpu-baseline --no-table --steps 300 --warmup 20 --e2e-steps 2 >> gpurun_out/${tag}_${wl}_pre.jsonl 2>> gpurun_out/${tag}_${wl}.err
   done
   ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,dram__bytes_read.sum,dram__bytes_write.sum,sm__warps_active.avg.pct_of_peak_sustained_active,launch__registers_per_thread,smsp__thread_inst_executed_per_inst_executed.ratio \
-    --clock-control none -k regex:'nsgym_spec_kernel|step_kernel' -s 40 -c 3 --csv --log-file gpurun_out/${tag}_${wl}_ncu.csv \
+    --clock-control none -k regex:'nsgym_spec_|step_kernel' -s 40 -c 3 --csv --log-file gpurun_out/${tag}_${wl}_ncu.csv \
     python bench.py --workload $wl --no-cpu-baseline --no-table --steps 60 --warmup 3 --e2e-steps 2 > gpurun_out/${tag}_${wl}_ncu.log 2>&1
 done
 python - <<PY

@@ -27,7 +27,7 @@ for f in sorted(glob.glob("gpurun_out/${tag}_*.jsonl")):
         print(f.split("/")[-1], "%.3e steps/s" % d["value"], "%.1f us" % r["kernel_us_per_launch"], "frac %.3f" % r["frac"], d["config"]["kernels"][:22], d["clocks"]["sm_mhz"], d["clocks"]["reasons"])
 PY
 # full capture of the specialised C1 kernel (steady state: skip the first launches)
-ncu --set full --import-source on --clock-control none -k regex:nsgym_spec_kernel -s 30 -c 1 -o gpurun_out/${tag}_full_c1_spec -f \
+ncu --set full --import-source on --clock-control none -k regex:nsgym_spec_ -s 30 -c 1 -o gpurun_out/${tag}_full_c1_spec -f \
   python bench.py --workload c1_cartpole --no-cpu-baseline --no-table --steps 40 --warmup 3 --e2e-steps 2 > gpurun_out/${tag}_full_c1.log 2>&1
 ncu -i gpurun_out/${tag}_full_c1_spec.ncu-rep --page details > gpurun_out/${tag}_full_c1_spec.txt 2>&1
 ncu -i gpurun_out/${tag}_full_c1_spec.ncu-rep --page source --csv > gpurun_out/${tag}_full_c1_spec_source.csv 2>&1
