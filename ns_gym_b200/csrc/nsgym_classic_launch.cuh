@@ -137,15 +137,16 @@ template <typename R>
 static void row_words(const SlotT<R>& b, const NsgymSlot& a, int32_t (&iw)[kRowInt], double (&rw)[kRowReal],
                       double (&dw)[kRowDbl]) {
   int flags = b.flags;
-  int mod = 0;
+  int mod_d = 0, mod_on_enc = 0;
   if (!(flags & SF_SLOW_SCHED)) {
-    const int on = b.mod_on == INT32_MAX ? 0xFFFF : (b.mod_on < 0 ? 0 : b.mod_on);
-    if (b.mod_d > 0xFFFF || (b.mod_on != INT32_MAX && b.mod_on >= 0xFFFF)) flags |= SF_SLOW_SCHED;   // does not pack
-    else mod = b.mod_d | (on << 16);
+    // the fast modulo as (modulus, on-count + 1 | 0 = always); a pair that does not fit 16 bits each takes
+    // the slow scheduler switch instead
+    if (b.mod_d > 0xFFFF || (b.mod_on != INT32_MAX && (b.mod_on < 0 || b.mod_on >= 0xFFFF))) flags |= SF_SLOW_SCHED;
+    else { mod_d = b.mod_d; mod_on_enc = b.mod_on == INT32_MAX ? 0 : b.mod_on + 1; }
   }
-  iw[RI_OPS] = flags | (a.sched_op << 8) | (a.upd_op << 16);
+  iw[RI_OPS] = flags | (a.sched_op << 5) | (a.upd_op << 9);
   iw[RI_START] = b.start; iw[RI_SPAN] = b.span;
-  iw[RI_MOD] = mod; iw[RI_MAGIC] = (flags & SF_SLOW_SCHED) ? 0 : b.mod_magic;
+  iw[RI_MODD] = mod_d; iw[RI_MODON] = mod_on_enc;
   iw[RI_SI0] = a.si[0]; iw[RI_SI1] = a.si[1]; iw[RI_UI0] = a.ui[0]; iw[RI_UI1] = a.ui[1];
   iw[RI_IINIT] = a.istate_init;
   if (flags & (SF_SLOW_UPD | SF_MEDIUM)) {
@@ -166,7 +167,7 @@ static HetT<R, NP> build_het(const RowTable& t) {
   for (int j = 0; j < NP; ++j) {
     H.mask[j] = t.mask[j];
     for (int w = 0; w < kRowWords; ++w) H.plane[j][w] = t.plane[j][w];
-    for (int w = 0; w < kRowInt; ++w) H.idef[j][w] = t.def_int[j][w];
+    for (int w = 0; w < kRowInt; ++w) { H.idef[j][w] = t.def_int[j][w]; H.shift[j][w] = t.shift[j][w]; H.bits[j][w] = t.bits[j][w]; }
     for (int w = 0; w < kRowReal; ++w) H.rdef[j][w] = R(t.def_real[j][w]);
     for (int w = 0; w < kRowDbl; ++w) H.ddef[j][w] = t.def_dbl[j][w];
   }
@@ -221,7 +222,7 @@ static std::string spec_prelude(const char* header, const StepIO<R>& io, bool ro
   return std::string("#include \"") + header + "\"\nnamespace nsg {\ntemplate <int N> struct SpecWords { uint32_t w[N]; };\n" +
          "struct SpecFix { static constexpr int prefetch = " + std::to_string(io.prefetch ? 1 : 0) +
          ", want_delta = " + std::to_string(io.delta ? 1 : 0) + ", has_obs = " + std::to_string(io.obs ? 1 : 0) +
-         ", root = " + std::to_string(root ? 1 : -1) + "; };\n";
+         ", root = " + std::to_string(root ? 1 : -1) + ", rows_early = 1; };\n";
 }
 template <typename R>
 static uint32_t spec_facts(const StepIO<R>& io, bool root) {
@@ -277,8 +278,10 @@ static std::string spec_step_rows_source(const ProgramT<R, NP>& P, const HetT<R,
        spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
   s += spec_rows_source<R, NP>(H);
   s += "extern \"C\" __global__ void __launch_bounds__(256, NSGYM_HET_LEAN_MIN_BLOCKS)\nnsgym_spec_classic_step_rows("
-       "const __grid_constant__ nsg::StepIO<" + real + "> io, const __grid_constant__ nsg::HetPtrs hp) {\n"
-       "  constexpr nsg::" + prog + " P = nsg::spec_program();\n" + spec_rows_object(real, NP) +
+       "const __grid_constant__ nsg::StepIO<" + real + "> io, const __grid_constant__ nsg::HetPtrs hp, "
+       "const __grid_constant__ nsg::PoolPtrs pp) {\n"
+       "  constexpr nsg::" + prog + " P0 = nsg::spec_program();\n  nsg::" + prog + " P = P0;\n"
+       "  P.pool_f = pp.pool_f; P.pool_i = pp.pool_i; P.bitmap = pp.bitmap;\n" + spec_rows_object(real, NP) +
        "  nsg::classic_step_het_body<" + real + ", " + std::to_string(KIND) + ", " + std::to_string(NP) +
        ", true, nsg::SpecFix>(P, H, io);\n}\n";
   return s;
@@ -331,7 +334,8 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
         }
         if (k) {
           HetPtrs hp{H.ints, H.reals, H.dbls};
-          void* args[] = {const_cast<StepIO<R>*>(&io), &hp};
+          PoolPtrs pp{P.pool_f, P.pool_i, P.bitmap};
+          void* args[] = {const_cast<StepIO<R>*>(&io), &hp, &pp};
           if (a.specialized) *a.specialized = 1;
           return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
         }

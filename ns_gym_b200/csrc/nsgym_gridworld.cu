@@ -36,7 +36,7 @@ static HetT<double, MAXP> build_het_by_index(const NsgymSpec& spec, const RowTab
     if (q < 0 || q >= MAXP) continue;
     H.mask[q] = t.mask[j];
     for (int w = 0; w < kRowWords; ++w) H.plane[q][w] = t.plane[j][w];
-    for (int w = 0; w < kRowInt; ++w) H.idef[q][w] = t.def_int[j][w];
+    for (int w = 0; w < kRowInt; ++w) { H.idef[q][w] = t.def_int[j][w]; H.shift[q][w] = t.shift[j][w]; H.bits[q][w] = t.bits[j][w]; }
     for (int w = 0; w < kRowReal; ++w) H.rdef[q][w] = t.def_real[j][w];
     for (int w = 0; w < kRowDbl; ++w) H.ddef[q][w] = t.def_dbl[j][w];
   }

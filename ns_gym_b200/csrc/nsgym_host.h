@@ -36,6 +36,8 @@ struct RowTable {
   int n_int = 0, n_real = 0, n_dbl = 0;     // plane counts
   uint32_t mask[NSGYM_MAX_SLOTS] = {};
   uint8_t plane[NSGYM_MAX_SLOTS][kRowWords] = {};
+  uint8_t shift[NSGYM_MAX_SLOTS][kRowInt] = {};   // int words are bit-packed: field position / width in their plane
+  uint8_t bits[NSGYM_MAX_SLOTS][kRowInt] = {};
   int32_t def_int[NSGYM_MAX_SLOTS][kRowInt] = {};
   double def_real[NSGYM_MAX_SLOTS][kRowReal] = {};
   double def_dbl[NSGYM_MAX_SLOTS][kRowDbl] = {};

@@ -4,6 +4,7 @@
 // words, and compared with env 0: a word that never differs stays a launch constant, a word
 // that differs somewhere becomes one coalesced plane [n_envs] in device memory.  The traffic a
 // heterogeneous step adds is therefore exactly the per-env information the batch carries.
+#include <climits>
 #include <cstdio>
 #include <cstring>
 #include <vector>
@@ -33,9 +34,11 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
   t.precision = std::is_same<R, double>::value ? NSGYM_F64 : NSGYM_F32;
   int32_t iw[kRowInt];
   double rw[kRowReal], dw[kRowDbl];
-  // ---- pass 1: validate, defaults from env 0, which words vary ----
+  // ---- pass 1: validate, defaults from env 0, which words vary, value range of the int words ----
+  int32_t lo[NSGYM_MAX_SLOTS][kRowInt], hi_v[NSGYM_MAX_SLOTS][kRowInt];
   for (int j = 0; j < np; ++j) {
     lower_row<R>(spec, rows[j], j, t.def_int[j], t.def_real[j], t.def_dbl[j]);
+    for (int w = 0; w < kRowInt; ++w) { lo[j][w] = INT32_MAX; hi_v[j][w] = INT32_MIN; }
   }
   for (int64_t e = 0; e < n; ++e) {
     for (int j = 0; j < np; ++j) {
@@ -65,11 +68,15 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
                                a.sched_op != NSGYM_SCHED_MEMORYLESS;
         const bool dist = a.upd_op >= NSGYM_UPD_D_NOP;
         const bool lean_upd = dist ? (a.upd_op != NSGYM_UPD_D_RANDOM && a.ui[2] == 0)
-                                   : !((iw[RI_OPS] & 0xFF) & SF_SLOW_UPD);
+                                   : !((iw[RI_OPS] & 0x1F) & SF_SLOW_UPD);
         t.lean = t.lean && det_sched && lean_upd;
       }
       uint32_t m = 0;
-      for (int w = 0; w < kRowInt; ++w) m |= (iw[w] != t.def_int[j][w]) ? (1u << w) : 0u;
+      for (int w = 0; w < kRowInt; ++w) {
+        m |= (iw[w] != t.def_int[j][w]) ? (1u << w) : 0u;
+        if (iw[w] < lo[j][w]) lo[j][w] = iw[w];
+        if (iw[w] > hi_v[j][w]) hi_v[j][w] = iw[w];
+      }
       for (int w = 0; w < kRowReal; ++w)
         m |= (std::memcmp(&rw[w], &t.def_real[j][w], sizeof(double)) != 0) ? (1u << (kRowInt + w)) : 0u;
       for (int w = 0; w < kRowDbl; ++w)
@@ -79,8 +86,22 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
   }
   // ---- plane assignment ----
   for (int j = 0; j < np; ++j) {
-    for (int w = 0; w < kRowInt; ++w)
-      if ((t.mask[j] >> w) & 1u) t.plane[j][w] = uint8_t(t.n_int++);
+    // int words: bit-packed, in word order, into the planes of this slot -- a word takes the bits its
+    // largest value over the batch needs (all 32 when it is negative somewhere)
+    int used = 32;                                      // bits taken in the current plane (32: open a new one)
+    for (int w = 0; w < kRowInt; ++w) {
+      if (!((t.mask[j] >> w) & 1u)) continue;
+      int bits = 32;
+      if (lo[j][w] >= 0) {
+        bits = 1;
+        while (bits < 32 && (uint32_t(hi_v[j][w]) >> bits) != 0u) ++bits;
+      }
+      if (used + bits > 32) { t.n_int++; used = 0; }
+      t.plane[j][w] = uint8_t(t.n_int - 1);
+      t.shift[j][w] = uint8_t(used);
+      t.bits[j][w] = uint8_t(bits);
+      used += bits;
+    }
     for (int w = 0; w < kRowReal; ++w)
       if ((t.mask[j] >> (kRowInt + w)) & 1u) t.plane[j][kRowInt + w] = uint8_t(t.n_real++);
     for (int w = 0; w < kRowDbl; ++w)
@@ -104,7 +125,8 @@ int build_rows_t(const NsgymSpec& spec, const NsgymSlot* rows, RowTable* out, ch
       lower_row<R>(spec, rows[e * np + j], j, iw, rw, dw);
       const uint32_t m = t.mask[j];
       for (int w = 0; w < kRowInt; ++w)
-        if ((m >> w) & 1u) hi[size_t(t.plane[j][w]) * n + e] = iw[w];
+        if ((m >> w) & 1u)
+          hi[size_t(t.plane[j][w]) * n + e] |= int32_t(uint32_t(iw[w]) << t.shift[j][w]);
       for (int w = 0; w < kRowReal; ++w)
         if ((m >> (kRowInt + w)) & 1u) hr[size_t(t.plane[j][kRowInt + w]) * n + e] = R(rw[w]);
       for (int w = 0; w < kRowDbl; ++w)
