@@ -472,17 +472,43 @@ int nsgym_step(NsgymHandle* h, const void* d_action, const double* d_inj_uniform
   return 0;
 }
 
+static int ensure_streams(NsgymHandle* h) {
+  if (!h->streams_ready) {
+    for (auto& s : h->streams) NSG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
+    NSG_CUDA(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
+    h->streams_ready = true;
+  }
+  return 0;
+}
+
 int nsgym_step_many(NsgymHandle* const* handles, const void* const* d_actions, int n, int skip_updates, void* stream) {
   if (!handles || n <= 0) return fail(-1, "no handles");
   for (int k = 0; k < n; ++k) {
     if (!handles[k] || !handles[k]->bound) return fail(-1, "handle %d not bound", k);
     if (!handles[k]->initialised) return fail(-4, "handle %d: step before reset", k);
   }
-  // back-to-back launches from one host call: a batch of several env kinds (BASELINE config C4) pays the
-  // host-side cost of a step once, and the kernels queue without gaps
-  for (int k = 0; k < n; ++k)
-    if (int rc = nsgym_step(handles[k], d_actions ? d_actions[k] : nullptr, nullptr, nullptr, skip_updates, stream))
+  // One host call for a batch of several env kinds (BASELINE config C4): the host-side cost of a step is
+  // paid once, and the shards' kernels run CONCURRENTLY -- shard 0 on the caller's stream, every other shard
+  // on a stream of its own, forked from and joined back into the caller's stream with events -- so the tail
+  // of one kernel overlaps the head of the next instead of leaving SMs idle between two short launches.
+  cudaStream_t s0 = static_cast<cudaStream_t>(stream);
+  if (n > 1) {
+    for (int k = 0; k < n; ++k)
+      if (int rc = ensure_streams(handles[k])) return rc;
+    NSG_CUDA(cudaEventRecord(handles[0]->host_event, s0));
+  }
+  for (int k = 0; k < n; ++k) {
+    cudaStream_t sk = k == 0 ? s0 : handles[k]->streams[0];
+    if (k > 0) NSG_CUDA(cudaStreamWaitEvent(sk, handles[0]->host_event, 0));
+    if (int rc = nsgym_step(handles[k], d_actions ? d_actions[k] : nullptr, nullptr, nullptr, skip_updates, sk)) {
+      for (int q = 1; q <= k; ++q) cudaStreamSynchronize(handles[q]->streams[0]);
       return rc;
+    }
+    if (k > 0) {
+      NSG_CUDA(cudaEventRecord(handles[k]->host_event, sk));
+      NSG_CUDA(cudaStreamWaitEvent(s0, handles[k]->host_event, 0));
+    }
+  }
   return 0;
 }
 
@@ -502,11 +528,7 @@ int nsgym_step_host(NsgymHandle* h, const void* h_action, const NsgymHostOut* ou
   if (!h || !h->bound) return fail(-1, "handle not bound");
   if (!h->initialised) return fail(-4, "step before reset");
   if (!h_action || !out) return fail(-1, "NULL argument");
-  if (!h->streams_ready) {
-    for (auto& s : h->streams) NSG_CUDA(cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking));
-    NSG_CUDA(cudaEventCreateWithFlags(&h->host_event, cudaEventDisableTiming));
-    h->streams_ready = true;
-  }
+  if (int rc = ensure_streams(h)) return rc;
   // order the pipeline after whatever the caller's stream still has in flight on this handle's
   // buffers (a reset, a device-side step, a planning copy): the side streams are non-blocking
   // streams and would not wait for it by themselves
