@@ -1,6 +1,8 @@
 // nsgym_classic_launch.cuh -- host launcher for the classic-control kernels, instantiated
 // once per precision (nsgym_f32.cu with FMA contraction, nsgym_f64.cu with -fmad=false).
 #pragma once
+#include <cstdint>
+#include <cstdlib>
 #include <limits>
 #include <string>
 #include <type_traits>
@@ -248,6 +250,25 @@ static std::string spec_step_source(const ProgramT<R, NP>& P, int level, const S
   return s;
 }
 
+// Can the tiled kernels stream this launch's planes with TMA bulk copies?  Every plane offset must be a
+// multiple of 16 bytes: base pointers, the sub-range start and the plane stride (n envs).
+template <typename R>
+static bool tiled_ok(const StepIO<R>& io, bool kind_supported) {
+  static const bool off = [] { const char* e = std::getenv("NSGYM_B200_NO_TILED"); return e && *e && *e != '0'; }();
+  if (off || !kind_supported || io.count < 256u * 64u) return false;
+  auto al = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; };
+  return (io.n % 4u) == 0 && (io.begin % 4u) == 0 && al(io.state) && al(io.theta) && al(io.t) && al(io.istate) && al(io.action);
+}
+// tiles a block advances back to back (NSGYM_B200_TILES overrides): measured on 2^24 envs (Bridge /
+// FrozenLake, 5 resident blocks): 2 tiles 0.91 / 0.84 of the copy peak, 4: 0.985 / 0.93, 6: 0.985 / 0.95,
+// 16: 0.90 / 0.81; smaller batches keep at least ~3 waves of blocks
+static int tiles_per_block_for(uint32_t full_tiles) {
+  static const int forced = [] { const char* e = std::getenv("NSGYM_B200_TILES"); return e ? std::atoi(e) : 0; }();
+  if (forced > 0) return forced;
+  const int t = int(full_tiles / 2220u);
+  return t < 2 ? 2 : (t > 6 ? 6 : t);
+}
+
 // `spec_rows()`: the row layout (which words vary, their planes, the shared defaults) as a constant
 template <typename R, int NP>
 static std::string spec_rows_source(const HetT<R, NP>& H) {
@@ -379,6 +400,9 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       if (a.spec_cache) a.spec_cache->put(facts, k);
     }
     if (k) {
+      // (a tiled variant with TMA-prefetched planes, as the gridworld kernels have, was measured for the
+      // classic-control kernels too: no gain -- C1 fp32 166 -> 171 us, fp64 CartPole +2.5 %, the others
+      // -1..-3 % -- their record is one 128-bit load and three words, and they already run at full occupancy)
       void* args[] = {const_cast<StepIO<R>*>(&io)};
       if (a.specialized) *a.specialized = 1;
       return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(lean_grid), dim3(block), args, 0, stream);

@@ -1,6 +1,8 @@
 // Gridworld kernels (FrozenLake / CliffWalking / Bridge).  Probabilities are always fp64 and
 // this unit is built with -fmad=false: cumulative sums and W1 distances match NumPy exactly.
+#include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 
@@ -67,6 +69,22 @@ static std::string spec_grid_step_source(const GridProgram<MAXP>& G, const StepI
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
        "  nsg::grid_step_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
        ", false, nsg::SpecFix>(G, io);\n}\n";
+  return s;
+}
+
+// the tiled single-step kernel (grid_step_body_tiled): TMA bulk copies stream the planes of the next tiles
+// into shared memory while the block advances the current one
+template <int KIND, int D, int MAXP>
+static std::string spec_grid_step_tiled_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root) {
+  const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
+  std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
+  s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::grid_tiled_min_blocks<" + std::to_string(KIND) +
+       ">())\nnsgym_spec_grid_step_tiled(const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs, "
+       "int tiles_per_block) {\n"
+       "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
+       "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
+       "  nsg::grid_step_body_tiled<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
+       ", nsg::SpecFix>(G, io, tiles_per_block);\n}\n";
   return s;
 }
 
@@ -177,9 +195,33 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     }
     if (k) {
       GridPtrs ptrs{G.base.pool_f, G.base.pool_i, G.base.bitmap, G.tab};
-      void* args[] = {const_cast<StepIO<double>*>(&io), &ptrs};
       if (a.specialized) *a.specialized = 1;
-      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
+      // full tiles of 256 envs through the tiled kernel (TMA-prefetched planes) when every plane is 16-byte
+      // aligned; the remainder, and everything else, through the one-thread-one-env kernel
+      StepIO<double> rest = io;
+      const uint32_t full_tiles = tiled_ok(io, MAXP == 1) ? io.count / 256u : 0u;
+      if (full_tiles) {
+        cudaKernel_t kt = nullptr;
+        const uint32_t tfacts = facts | 512u;
+        if (!a.spec_cache || !a.spec_cache->find(tfacts, &kt)) {
+          kt = jit::kernel(spec_grid_step_tiled_source<KIND, D, MAXP>(G, io, root), "nsgym_spec_grid_step_tiled", false, nullptr);
+          if (a.spec_cache) a.spec_cache->put(tfacts, kt);
+        }
+        if (kt) {
+          StepIO<double> head = io;
+          head.count = full_tiles * 256u;
+          int tiles_per_block = tiles_per_block_for(full_tiles);
+          void* targs[] = {&head, &ptrs, &tiles_per_block};
+          const unsigned tgrid = (full_tiles + unsigned(tiles_per_block) - 1) / unsigned(tiles_per_block);
+          cudaError_t e = cudaLaunchKernel(reinterpret_cast<const void*>(kt), dim3(tgrid), dim3(256), targs, 0, stream);
+          if (e != cudaSuccess) return e;
+          rest.begin += head.count;
+          rest.count -= head.count;
+          if (rest.count == 0) return cudaSuccess;
+        }
+      }
+      void* args[] = {&rest, &ptrs};
+      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((rest.count + block - 1) / block), dim3(block), args, 0, stream);
     }
   }
   if (op == OP_ROLLOUT && !slow && !a.policy && (a.specialize || a.spec_source)) {

@@ -201,3 +201,23 @@ def test_specialised_row_kernels_equal_precompiled_row_kernels(name, precision):
             elif k < 6:
                 np.testing.assert_allclose(x[key].cpu().numpy(), y[key].cpu().numpy(), rtol=2e-4, atol=2e-5,
                                            err_msg=f"{name}: {key} step {k}")
+
+
+@pytest.mark.parametrize("n", [32768 + 100, 65536, 32768 + 101])
+@pytest.mark.parametrize("name", ["c5_bridge_uniform", "c2_frozenlake8_stepchange", "frozenlake8_cyclic_stale",
+                                  "cliff_drift", "bridge_stepwise"])
+def test_tiled_gridworld_kernels_equal_precompiled_kernels(name, n):
+    """Batches of >= 16384 envs run the tiled specialised kernel (TMA bulk copies prefetch the planes of the
+    next tiles into shared memory) on their full tiles of 256 envs and the one-thread-one-env kernel on the
+    remainder (n = 32768 + 100); a batch whose plane stride is not a multiple of 16 bytes (n odd) cannot
+    be streamed and keeps the plain kernel.  All must equal the precompiled lean kernel bit for bit."""
+    import torch
+
+    case = CASES[name]
+    info = {}
+    spec = _run(case, "fp64", False, n=n, steps=24, specialize=1, info=info)
+    lean = _run(case, "fp64", False, n=n, steps=24, specialize=0)
+    assert all(info["specialized"])
+    for k, (x, y) in enumerate(zip(spec, lean)):
+        for key in x:
+            assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
