@@ -9,3 +9,4 @@ python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/${tag}_ref.lo
 python tools/collect_traffic.py > gpurun_out/${tag}_traffic.log 2>&1; tail -3 gpurun_out/${tag}_traffic.log
 bash tools/bench_all.sh > gpurun_out/${tag}_bench_all.txt 2>&1; cat gpurun_out/${tag}_bench_all.txt
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv python bench.py --steps 20 --warmup 3 --no-cpu-baseline --no-table > gpurun_out/${tag}_launches.log 2>&1
+for wl in c5_bridge c2_frozenlake8_16m c4_hetero; do bash tools/gpu_full.sh $tag $wl; done
