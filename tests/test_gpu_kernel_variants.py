@@ -222,3 +222,17 @@ def test_tiled_gridworld_kernels_equal_precompiled_kernels(name, n):
     for k, (x, y) in enumerate(zip(spec, lean)):
         for key in x:
             assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {16 - len(spec) + k}"
+
+
+def test_row_words_are_bit_packed():
+    """The varying int words of a per-env row are packed to the width the batch needs: a C4 CartPole slot
+    (opcode word, modulus, on-count, two pool offsets vary) takes 2 int planes + 5 coefficient planes = 28 B,
+    not 10 planes; the layout reports it and the algorithmic bytes per env-step follow."""
+    from tests import parity_util as pu
+
+    env = pu.gpu_env(CASES["c4_cartpole_rows"], 4096, precision="fp32", want_delta=True, want_obs=False)
+    rows = env.row_bytes_per_env
+    assert 0 < rows < 80, rows          # two slots; 80 B = one plane per varying word (round 1)
+    assert abs(env.bytes_per_step - (66 + 8 + rows)) < 1e-9
+    g = pu.gpu_env(CASES["c4_frozenlake8_rows"], 4096, precision="fp64")
+    assert 0 < g.row_bytes_per_env < 60, g.row_bytes_per_env      # 60 B unpacked

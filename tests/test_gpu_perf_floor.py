@@ -2,9 +2,11 @@
 BASELINE.md are checked by the driver's own `pytest -m gpu` run and not only by the builder.
 
 Each workload is timed at its bench batch size with CUDA events (bench.quick_measure: 5 warm-up + 30
-timed launches in 5 repetitions, median) and must reach 90 % of the value recorded in
+timed launches in 5 repetitions, median) and must reach 87 % of the value recorded in
 tests/perf_floors.json; single-step workloads with an ncu traffic figure (profiles/traffic.json) must
-also reach 90 % of the physical-DRAM fraction that value implies.  A throttled GPU (hw slowdown,
+also reach 87 % of the physical-DRAM fraction that value implies (the recorded values come from ONE box;
+boxes of this pool differ by up to 7 % on the same kernel -- C1 in rounds 1 / 2: 8.4 .. 9.1e10 -- and the
+software power cap moves the fp64 kernels by another 5 %).  A throttled GPU (hw slowdown,
 thermal slowdown) invalidates the measurement: the test then skips instead of failing."""
 import json
 import os
@@ -17,6 +19,9 @@ pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
 with open(os.path.join(HERE, "perf_floors.json")) as f:
     FLOORS = {k: v for k, v in json.load(f).items() if not k.startswith("_")}
+
+
+FLOOR = 0.87
 
 
 def _throttle_reasons():
@@ -40,12 +45,12 @@ def test_workload_reaches_its_floor(workload):
     if reasons:
         pytest.skip(f"GPU throttled during the measurement: {reasons}")
     want = FLOORS[workload]
-    assert got["steps_per_s"] >= 0.9 * want, (
-        f"{workload}: {got['steps_per_s']:.3e} env-steps/s < 90 % of the recorded {want:.3e} "
+    assert got["steps_per_s"] >= FLOOR * want, (
+        f"{workload}: {got['steps_per_s']:.3e} env-steps/s < {FLOOR:.0%} of the recorded {want:.3e} "
         f"({got['us_per_launch']:.1f} us per launch)")
     if got.get("frac_physical") is not None:
         peak, _ = bench.load_peak()
         traffic = bench.load_traffic()[workload]
         implied = traffic * want / (got["envs"] * 1e9) / peak          # physical fraction at the recorded rate
-        assert got["frac_physical"] >= 0.9 * implied
+        assert got["frac_physical"] >= FLOOR * implied
         assert got["frac_physical"] < 1.05, "faster than the measured copy peak: the kernel is not doing the work"
