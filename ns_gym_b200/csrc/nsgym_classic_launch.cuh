@@ -234,18 +234,27 @@ static uint32_t spec_facts(const StepIO<R>& io, bool root) {
 // The single-step kernel of a lean classic-control program: the body the precompiled kernel runs
 // (classic_step_body), with the lowered program rebuilt as a constexpr object from the words of the
 // host's ProgramHeadT and the launch facts fixed in SpecFix.
+// `pools`: a program with slow-class slots (level 2) reads its value lists / window lists / bitmaps through
+// the pool pointers, which stay kernel parameters
+static std::string spec_program_object(const std::string& prog, bool pools) {
+  if (!pools) return "  constexpr nsg::" + prog + " P = nsg::spec_program();\n";
+  return "  constexpr nsg::" + prog + " P0 = nsg::spec_program();\n  nsg::" + prog + " P = P0;\n"
+         "  P.pool_f = pp.pool_f; P.pool_i = pp.pool_i; P.bitmap = pp.bitmap;\n";
+}
 template <typename R, int KIND, int NP>
 static std::string spec_step_source(const ProgramT<R, NP>& P, int level, const StepIO<R>& io, bool root) {
   const std::string real = std::is_same<R, float>::value ? "float" : "double";
   const ProgramHeadT<R, NP>& head = P;
   const std::string prog = "ProgramT<" + real + ", " + std::to_string(NP) + ">";
   const std::string headt = "ProgramHeadT<" + real + ", " + std::to_string(NP) + ">";
+  const bool pools = level >= 2;
   std::string s = spec_prelude<R>("nsgym_device.cuh", io, root);
   s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
        spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
   s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::classic_spec_min_blocks<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(level) + ">())\nnsgym_spec_classic_step(const __grid_constant__ nsg::StepIO<" +
-       real + "> io) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n  nsg::classic_step_body<" + real + ", " +
+       real + "> io" + (pools ? ", const __grid_constant__ nsg::PoolPtrs pp" : "") + ") {\n" + spec_program_object(prog, pools) +
+       "  nsg::classic_step_body<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", nsg::SpecFix>(P, io);\n}\n";
   return s;
 }
@@ -319,8 +328,10 @@ static std::string spec_rollout_source(const ProgramT<R, NP>& P, int level, cons
   std::string s = spec_prelude<R>("nsgym_device.cuh", io, root);
   s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
        spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
+  const bool pools = level >= 2;
   s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_classic_rollout(const __grid_constant__ nsg::StepIO<" + real +
-       "> io, const __grid_constant__ nsg::RolloutArgs ra) {\n  constexpr nsg::" + prog + " P = nsg::spec_program();\n"
+       "> io, const __grid_constant__ nsg::RolloutArgs ra" + (pools ? ", const __grid_constant__ nsg::PoolPtrs pp" : "") +
+       ") {\n" + spec_program_object(prog, pools) +
        "  const nsg::HetT<" + real + ", " + std::to_string(NP) + "> no_rows{};\n  nsg::classic_rollout_body<" + real + ", " +
        std::to_string(KIND) + ", " + std::to_string(NP) + ", " + std::to_string(level) + ", false, " + (lin ? "true" : "false") +
        ", nsg::SpecFix>(P, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, static_cast<const float*>(ra.pol), ra.pol_per_env);\n}\n";
@@ -389,7 +400,11 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
   constexpr bool kHasMedium = true;
   const unsigned lean_grid = unsigned((a.count + block * NSGYM_LEAN_EPT - 1) / (block * NSGYM_LEAN_EPT));
   if (a.specialized) *a.specialized = 0;
-  if (op == OP_STEP && level < 2 && (a.specialize || a.spec_source)) {
+  // programs with slow-class slots specialise too (level 2: the rule switches fold to the one rule of each slot);
+  // injected tables and NSGYM_OPT_GENERAL_KERNELS keep the precompiled general kernel
+  const bool spec_ok = level < 2 || (P.n_slow > 0 && !a.inj_u && !a.inj_z && !a.general_kernels);
+  PoolPtrs pp{P.pool_f, P.pool_i, P.bitmap};
+  if (op == OP_STEP && spec_ok && (a.specialize || a.spec_source)) {
     // lean program: the kernel compiled for exactly this program (cached per distinct source)
     const bool root = a.plan_elapsed < 0 && !a.skip_updates;
     const uint32_t facts = uint32_t(level) | spec_facts(io, root);
@@ -404,12 +419,12 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       // (a tiled variant with TMA-prefetched planes, as the gridworld kernels have, was measured for the
       // classic-control kernels too: no gain -- C1 fp32 166 -> 171 us, fp64 CartPole +2.5 %, the others
       // -1..-3 % -- their record is one 128-bit load and three words, and they already run at full occupancy)
-      void* args[] = {const_cast<StepIO<R>*>(&io)};
+      void* args[] = {const_cast<StepIO<R>*>(&io), &pp};      // (pp: level 2 only -- a lean kernel takes one parameter)
       if (a.specialized) *a.specialized = 1;
-      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(lean_grid), dim3(block), args, 0, stream);
+      return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(level < 2 ? lean_grid : grid), dim3(block), args, 0, stream);
     }
   }
-  if (op == OP_ROLLOUT && level < 2 && NP > 0 && (a.specialize || a.spec_source)) {
+  if (op == OP_ROLLOUT && spec_ok && NP > 0 && (a.specialize || a.spec_source)) {
     const bool root = a.plan_elapsed < 0 && !a.skip_updates;
     const bool lin = a.policy != nullptr;
     const uint32_t facts = uint32_t(level) | spec_facts(io, root) | 64u | (lin ? 128u : 0u);
@@ -422,7 +437,7 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
     }
     if (k) {
       RolloutArgs ra{a.k_steps, a.gamma, a.ret, a.len, a.policy, a.policy_per_env};
-      void* args[] = {const_cast<StepIO<R>*>(&io), &ra};
+      void* args[] = {const_cast<StepIO<R>*>(&io), &ra, &pp};
       if (a.specialized) *a.specialized = 1;
       return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);
     }

@@ -94,19 +94,26 @@ def test_lean_kernels_track_general_kernels_fp32(name):
 # ---- program as a compile-time constant, against the precompiled lean kernels on the same native draws
 SPECIALISING = ["c1_cartpole_readme", "cartpole_silent", "cartpole_persistent", "c3_acrobot", "c3_mountaincar",
                 "c3_pendulum", "mountaincar_continuous", "mountaincar_constraint", "acrobot_constraints"]
+# programs with slow-class slots (stochastic schedulers, list / cursor rules, OU / bounded random walks, ...):
+# general kernel class, specialised with the slow class unrolled over the slots
+SPECIALISING_SLOW = ["cartpole_lists", "cartpole_stochastic", "cartpole_stochastic_scheds", "cartpole_custom_sched",
+                     "cartpole_memoryless_lists", "cartpole_all_params"]
 SPECIALISING_GRID = ["c2_frozenlake8_drift", "c2_frozenlake8_stepchange", "frozenlake8_lerp", "frozenlake8_cyclic_stale",
                      "cliff_terminal", "cliff_drift", "c5_bridge_uniform", "c5_bridge_split", "bridge_stepwise"]
 
 
 def _assert_specialised_where_lean(name, info):
-    """Programs of the lean kernel classes run the specialised kernel; a program with a slow-class slot
-    (cartpole_persistent: CyclicUpdate) keeps the general kernel."""
+    """Every native-draw program of these lists runs a specialised kernel: the lean classes, and -- with the
+    slow class unrolled over the slots -- programs with cursor / list rules too (cartpole_persistent:
+    CyclicUpdate, general kernel class)."""
     from ns_gym_b200 import native as nv
 
-    lean = [c in (nv.KERNEL_LEAN_FAST, nv.KERNEL_LEAN_MEDIUM) for c in info["class"]]
-    assert info["specialized"] == lean, f"{name}: specialised {info['specialized'][:3]} vs lean class {lean[:3]}"
-    if name != "cartpole_persistent":
-        assert all(lean), f"{name}: expected a lean program"
+    assert all(info["specialized"]), f"{name}: the specialised kernel did not run"
+    want = nv.KERNEL_GENERAL if name == "cartpole_persistent" else None
+    if want is not None:
+        assert all(c == want for c in info["class"])
+    else:
+        assert all(c in (nv.KERNEL_LEAN_FAST, nv.KERNEL_LEAN_MEDIUM) for c in info["class"]), info["class"][:3]
 
 
 @pytest.mark.parametrize("name", ["frozenlake8_cyclic_stale", "bridge_stepwise", "c5_bridge_uniform"])
@@ -236,3 +243,29 @@ def test_row_words_are_bit_packed():
     assert abs(env.bytes_per_step - (66 + 8 + rows)) < 1e-9
     g = pu.gpu_env(CASES["c4_frozenlake8_rows"], 4096, precision="fp64")
     assert 0 < g.row_bytes_per_env < 60, g.row_bytes_per_env      # 60 B unpacked
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("name", SPECIALISING_SLOW)
+def test_specialised_general_class_kernels_equal_precompiled_kernels(name, precision):
+    """Programs with slow-class slots on native draws: the specialised kernel (level 2, slow class unrolled over
+    the slots, no injection code) against the precompiled general kernel -- fp64 bit for bit, fp32 to rounding."""
+    import torch
+
+    from ns_gym_b200 import native as nv
+
+    if name not in CASES:
+        pytest.skip(f"no case {name}")
+    case = CASES[name]
+    info = {}
+    steps = 40 if precision == "fp64" else 6
+    spec = _run(case, precision, False, specialize=1, info=info, steps=steps)
+    pre = _run(case, precision, False, specialize=0, steps=steps)
+    assert all(info["specialized"]) and all(c == nv.KERNEL_GENERAL for c in info["class"])
+    for k, (x, y) in enumerate(zip(spec, pre)):
+        for key in x:
+            if precision == "fp64" or (k == 0 and key in ("flags", "change", "t", "istate")):
+                assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+            elif key in ("state", "theta", "reward", "obs", "delta"):
+                np.testing.assert_allclose(x[key].cpu().numpy(), y[key].cpu().numpy(), rtol=2e-4, atol=2e-5,
+                                           err_msg=f"{name}: {key} step {k}")

@@ -38,10 +38,7 @@ def test_every_lean_classic_case_specialises(name, precision):
     c = CASES[name]
     p = compile_program(c["env_id"], c["params"](S, U), 16, precision=precision, **c["wrapper"], **c["make"])
     rc, src, log, err = _check(p.spec, 1, 1)
-    if rc == -2:        # slow rule classes: no specialised kernel, by design
-        assert "does not specialise" in err
-        return
-    assert rc > 0, (name, rc, err, log)
+    assert rc > 0, (name, rc, err, log)     # lean classes and programs with slow-class slots alike
     real = "float" if precision == "fp32" else "double"
     assert f"nsg::StepIO<{real}>" in src and "want_delta = 1" in src
     if len(c["params"](S, U)):     # the fused rollout of the same program
