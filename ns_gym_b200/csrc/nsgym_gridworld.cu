@@ -60,15 +60,17 @@ static std::string spec_grid_program_source(const GridProgram<MAXP>& G) {
 // The single-step kernel of a lean gridworld program (deterministic schedulers and rules): grid_step_body
 // with everything but the four device pointers of the program as a compile-time constant.
 template <int KIND, int D, int MAXP>
-static std::string spec_grid_step_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root) {
+static std::string spec_grid_step_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root, bool slow = false) {
   const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
   std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
-  s += "extern \"C\" __global__ void __launch_bounds__(256, nsg::grid_spec_min_blocks<" + std::to_string(KIND) +
-       ">())\nnsgym_spec_grid_step(const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs) {\n"
+  // (slow: stochastic schedulers / Dirichlet draws / the Lipschitz loop -- the general class, 4 resident blocks)
+  s += "extern \"C\" __global__ void __launch_bounds__(256, " +
+       (slow ? std::string("4") : "nsg::grid_spec_min_blocks<" + std::to_string(KIND) + ">()") +
+       ")\nnsgym_spec_grid_step(const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs) {\n"
        "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
        "  nsg::grid_step_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
-       ", false, nsg::SpecFix>(G, io);\n}\n";
+       ", " + (slow ? "true" : "false") + ", nsg::SpecFix>(G, io);\n}\n";
   return s;
 }
 
@@ -108,7 +110,7 @@ static std::string spec_grid_step_rows_source(const GridProgram<MAXP>& G, const 
 
 // K fused steps of a lean gridworld program under the uniform-random policy (grid_rollout_body)
 template <int KIND, int D, int MAXP>
-static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root) {
+static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root, bool slow = false) {
   const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
   std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
   s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_grid_rollout(const __grid_constant__ nsg::StepIO<double> io, "
@@ -117,7 +119,7 @@ static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const St
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
        "  const nsg::HetT<double, " + std::to_string(MAXP) + "> no_rows{};\n"
        "  nsg::grid_rollout_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
-       ", false, false, false, nsg::SpecFix>(G, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, nullptr, 0);\n}\n";
+       ", " + (slow ? "true" : "false") + ", false, false, nsg::SpecFix>(G, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, nullptr, 0);\n}\n";
   return s;
 }
 
@@ -183,12 +185,15 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
   }
   const HetT<double, MAXP> no_rows{};
   if (a.specialized) *a.specialized = 0;
-  if (op == OP_STEP && !slow && (a.specialize || a.spec_source)) {
+  // programs with stochastic rules specialise as well (general class: every scheduler / rule switch folds to
+  // the slot's own); injected tables and NSGYM_OPT_GENERAL_KERNELS keep the precompiled general kernel
+  const bool spec_ok = !slow || (!a.inj_u && !a.general_kernels);
+  if (op == OP_STEP && spec_ok && (a.specialize || a.spec_source)) {
     const bool root = a.plan_elapsed < 0 && !a.skip_updates;
-    const uint32_t facts = spec_facts(io, root);
+    const uint32_t facts = spec_facts(io, root) | (slow ? 1024u : 0u);
     cudaKernel_t k = nullptr;
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
-      const std::string src = spec_grid_step_source<KIND, D, MAXP>(G, io, root);
+      const std::string src = spec_grid_step_source<KIND, D, MAXP>(G, io, root, slow);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
       k = jit::kernel(src, "nsgym_spec_grid_step", false, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);
@@ -199,7 +204,7 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
       // full tiles of 256 envs through the tiled kernel (TMA-prefetched planes) when every plane is 16-byte
       // aligned; the remainder, and everything else, through the one-thread-one-env kernel
       StepIO<double> rest = io;
-      const uint32_t full_tiles = tiled_ok(io, MAXP == 1) ? io.count / 256u : 0u;
+      const uint32_t full_tiles = tiled_ok(io, MAXP == 1 && !slow) ? io.count / 256u : 0u;
       if (full_tiles) {
         cudaKernel_t kt = nullptr;
         const uint32_t tfacts = facts | 512u;
@@ -224,12 +229,12 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
       return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((rest.count + block - 1) / block), dim3(block), args, 0, stream);
     }
   }
-  if (op == OP_ROLLOUT && !slow && !a.policy && (a.specialize || a.spec_source)) {
+  if (op == OP_ROLLOUT && spec_ok && !a.policy && (a.specialize || a.spec_source)) {
     const bool root = a.plan_elapsed < 0 && !a.skip_updates;
-    const uint32_t facts = spec_facts(io, root) | 64u;
+    const uint32_t facts = spec_facts(io, root) | 64u | (slow ? 1024u : 0u);
     cudaKernel_t k = nullptr;
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
-      const std::string src = spec_grid_rollout_source<KIND, D, MAXP>(G, io, root);
+      const std::string src = spec_grid_rollout_source<KIND, D, MAXP>(G, io, root, slow);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
       k = jit::kernel(src, "nsgym_spec_grid_rollout", false, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);

@@ -11,7 +11,9 @@ pytestmark = pytest.mark.gpu
 @pytest.mark.parametrize("name,precision,n,chunks", [
     ("c1_cartpole_readme", "fp32", 5000, 8), ("c1_cartpole_readme", "fp32", 257, 3), ("c1_cartpole_readme", "fp64", 4097, 1),
     ("c3_pendulum", "fp32", 3000, 5), ("c3_acrobot", "fp64", 1025, 4), ("c2_frozenlake8_drift", "fp64", 6001, 7),
-    ("c5_bridge_split", "fp64", 999, 16), ("c4_cartpole_rows", "fp32", 700, 3)])
+    ("c5_bridge_split", "fp64", 999, 16), ("c4_cartpole_rows", "fp32", 700, 3),
+    # chunks of >= 2^21 envs: every chunk runs the tiled (TMA-prefetched) specialised gridworld kernel on its sub-range
+    ("c5_bridge_uniform", "fp64", (1 << 22) + 512, 2), ("c1_cartpole_readme", "fp32", 1 << 17, 4)])
 def test_host_step_equals_device_step(name, precision, n, chunks):
     import torch
 
@@ -22,7 +24,7 @@ def test_host_step_equals_device_step(name, precision, n, chunks):
     dev_env.reset(seed=8)
     host_env.reset(seed=8)
     h_act, h_out = host_env.make_host_io()
-    for k in range(12):
+    for k in range(12 if n < (1 << 20) else 4):
         a = dev_env.action_space.sample()
         dev_env.step_raw(a)
         h_act.copy_(a.cpu())

@@ -269,3 +269,21 @@ def test_specialised_general_class_kernels_equal_precompiled_kernels(name, preci
             elif key in ("state", "theta", "reward", "obs", "delta"):
                 np.testing.assert_allclose(x[key].cpu().numpy(), y[key].cpu().numpy(), rtol=2e-4, atol=2e-5,
                                            err_msg=f"{name}: {key} step {k}")
+
+
+@pytest.mark.parametrize("name", ["frozenlake4_memoryless_cyclic", "cliff_random_categorical", "bridge_lipschitz_bounded"])
+def test_specialised_general_class_gridworld_kernels_equal_precompiled_kernels(name):
+    """Gridworld programs with stochastic schedulers / RandomCategorical / the Lipschitz-bounded wrapper on native
+    draws: specialised general-class kernel against the precompiled one, bit for bit."""
+    import torch
+
+    from ns_gym_b200 import native as nv
+
+    case = CASES[name]
+    info = {}
+    spec = _run(case, "fp64", False, specialize=1, info=info, steps=40)
+    pre = _run(case, "fp64", False, specialize=0, steps=40)
+    assert all(info["specialized"]) and all(c == nv.KERNEL_GENERAL for c in info["class"])
+    for k, (x, y) in enumerate(zip(spec, pre)):
+        for key in x:
+            assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
