@@ -105,6 +105,7 @@ def gpu_run(env, actions, u, z, first_row=1, do_reset=True):
         rec[k2] = np.stack(v)
     rec["_bad_dist"] = bad
     rec["_kernel_class"] = int(env.lib.nsgym_last_kernel_class(env._h))
+    rec["_specialized"] = bool(env.lib.nsgym_last_kernel_specialized(env._h))
     return rec
 
 

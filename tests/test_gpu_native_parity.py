@@ -23,7 +23,7 @@ SEED = 77
 N_ENVS = 64
 
 
-def _run(name, precision, steps, offset=0, **extra):
+def _run(name, precision, steps, offset=0, specialize=0, **extra):
     from ns_gym_b200 import native as nv
 
     case = CASES[name]
@@ -34,6 +34,7 @@ def _run(name, precision, steps, offset=0, **extra):
                                              replay=not persistent, gid_offset=offset)
     ref = pu.oracle_trace_streams(case, clock, per_env, actions)
     env = pu.gpu_env(case, N_ENVS, precision=precision, seed=SEED, env_id_offset=offset, **extra)
+    env.set_option("specialize", specialize)      # 1: the program-specialised kernels large batches run by default
     got = pu.gpu_run(env, actions, None, None)
     return ref, got, nv
 
@@ -48,11 +49,15 @@ LEAN_FP64 = [("c1_cartpole_readme", "LEAN_FAST"), ("cartpole_silent", "LEAN_FAST
              ("c4_cartpole_rows", "ROWS_LEAN"), ("het_cartpole_lean", "ROWS_LEAN"), ("c4_frozenlake8_rows", "ROWS_LEAN")]
 
 
+# specialize = 1: the kernels bench.py's large batches actually launch (compiled at run time around the program);
+# every kind of native-draw program specialises except batches with general (non-lean) per-env rows
+@pytest.mark.parametrize("specialize", [0, 1])
 @pytest.mark.parametrize("name,klass", LEAN_FP64)
-def test_native_draw_kernels_match_the_oracle_fp64(name, klass):
+def test_native_draw_kernels_match_the_oracle_fp64(name, klass, specialize):
     steps = min(CASES[name]["steps"], 120)
-    ref, got, nv = _run(name, "fp64", steps, offset=(1 << 32) + 12345)
+    ref, got, nv = _run(name, "fp64", steps, offset=(1 << 32) + 12345, specialize=specialize)
     assert got["_kernel_class"] == getattr(nv, "KERNEL_" + klass), (name, got["_kernel_class"])
+    assert got["_specialized"] == bool(specialize), name
     assert not got["_bad_dist"]
     pu.compare(ref, got, float_obs_rtol=1e-6, name=name)
 
@@ -62,13 +67,15 @@ FP32 = [("c1_cartpole_readme", "LEAN_FAST"), ("c3_acrobot", "LEAN_FAST"), ("c3_m
         ("cartpole_stochastic", "GENERAL")]
 
 
+@pytest.mark.parametrize("specialize", [0, 1])
 @pytest.mark.parametrize("name,klass", FP32)
-def test_native_draw_kernels_track_the_oracle_fp32(name, klass):
+def test_native_draw_kernels_track_the_oracle_fp32(name, klass, specialize):
     """The benched fp32 kernels (C1 headline: classic_step_kernel<float, CartPole, 2, 0>) on their own
     draws vs the fp64 oracle fed the same draws, each env up to its first episode end."""
     steps = min(CASES[name]["steps"], 60)
-    ref, got, nv = _run(name, "fp32", steps)
+    ref, got, nv = _run(name, "fp32", steps, specialize=specialize)
     assert got["_kernel_class"] == getattr(nv, "KERNEL_" + klass), (name, got["_kernel_class"])
+    assert got["_specialized"] == bool(specialize), name
     ended = (ref["terminated"] | ref["truncated"] | ref["was_reset"])
     alive = np.cumsum(ended, axis=0) == 0
     assert alive[:5].all() and alive.sum() > 10 * N_ENVS
