@@ -173,7 +173,8 @@ typedef struct {
   /* gridworld description (toy_text.py:426-469, :86-138; envs/Bridge.py:12,113-174) */
   int32_t nrow, ncol;
   uint64_t hole_mask, goal_mask, start_mask; /* bit = cell index; maps of <= 64 cells (else cell_class) */
-  int32_t start_cell;
+  int32_t start_cell;            /* -1 (FrozenLake): the map has several start cells, a reset samples one uniformly
+                                    (categorical_sample over them in row-major order, with this step's gridworld uniform) */
   int32_t split_mode;            /* Bridge: P_left / P_right by column of the current cell */
   float reward_f, reward_h, reward_g, reward_s; /* by destination cell letter */
   int32_t terminal_cliff;        /* CliffWalking */

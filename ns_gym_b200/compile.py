@@ -501,12 +501,14 @@ def compile_program(env_id: str, tunable_params: dict, n_envs: int, *, precision
             if desc is None:
                 desc = FROZEN_LAKE_MAPS[map_name or ("8x8" if env_id == "FrozenLake8x8-v1" else "4x4")]
             nrow, ncol, hole, goal, start, starts, letters = _grid_masks(desc)
-            if len(starts) != 1:
-                raise CompileError("FrozenLake maps with several start cells are not supported")
+            if len(starts) < 1:
+                raise CompileError("the FrozenLake map has no start cell 'S'")
             rw = {"F": 0.0, "H": 0.0, "G": 1.0, "S": 0.0}
             if modified_rewards:
                 rw = {k: float(modified_rewards[k]) for k in "FHGS"}
-            start_cell = starts[0]
+            # several 'S' cells: reset draws the start cell, categorical_sample(initial_state_distrib) over the
+            # start cells in row-major order (gymnasium FrozenLakeEnv.reset; toy_text.py:314-319 accepts any desc)
+            start_cell = starts[0] if len(starts) == 1 else -1
         elif kind == nv.ENV_CLIFFWALKING:
             nrow, ncol, letters = 4, 12, None
             hole = sum(1 << (3 * 12 + c) for c in range(1, 11))

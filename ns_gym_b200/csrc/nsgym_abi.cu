@@ -44,7 +44,7 @@ const KindInfo kKinds[NSGYM_ENV_COUNT] = {
 
 struct NsgymHandle {
   NsgymSpec spec;
-  nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr};
+  nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr, 0};
   NsgymBuffers buf{};
   bool bound = false;
   bool initialised = false;
@@ -160,7 +160,9 @@ int validate(const NsgymSpec* s) {
     if (s->n_dist != want) return fail(-1, "n_dist %d, this env needs %d", s->n_dist, want);
     if (s->nrow <= 0 || s->ncol <= 0 || s->nrow * s->ncol > 256)
       return fail(-1, "gridworld maps are limited to 256 cells (got %dx%d)", s->nrow, s->ncol);
-    if (s->start_cell < 0 || s->start_cell >= s->nrow * s->ncol) return fail(-1, "start_cell out of range");
+    // start_cell == -1: FrozenLake map with several 'S' cells, a reset samples one (toy_text.py:314-319 accepts any desc)
+    if (s->start_cell >= s->nrow * s->ncol || s->start_cell < -1 || (s->start_cell < 0 && s->env_kind != NSGYM_ENV_FROZENLAKE))
+      return fail(-1, "start_cell out of range");
     if (s->env_kind != NSGYM_ENV_BRIDGE && s->n_slots != 1) return fail(-1, "this env has exactly one parameter, P");
   } else if (s->precision != NSGYM_F32 && s->precision != NSGYM_F64) {
     return fail(-1, "precision must be NSGYM_F32 or NSGYM_F64");
@@ -355,7 +357,10 @@ int nsgym_create(const NsgymSpec* spec, NsgymHandle** out) {
   if (!rc) rc = upload(spec->pool_i, spec->n_pool_i, &h->pools.pool_i);
   if (!rc) rc = upload(spec->bitmap, spec->n_bitmap_words, &h->pools.bitmap);
   if (!rc && h->grid()) {
-    uint32_t words[328];
+    NsgymSpec with_map = *spec;                       // (h->spec keeps no host pointers)
+    h->pools.grid_n_start = nsg::resolve_start_cells(&with_map);
+    h->spec.start_cell = with_map.start_cell;
+    uint32_t words[nsg::kGridTabWords];
     char err[256] = "";
     const int n_words = nsg::build_grid_tables(*spec, words, err, sizeof err);
     rc = n_words < 0 ? fail(-1, "%s", err) : upload(words, n_words, &h->pools.grid_tab);
@@ -874,7 +879,8 @@ int nsgym_jit_check(const NsgymSpec* spec, int rollout, int want_delta, int want
   if (want_obs) io.obs = marker;
   std::string src;
   io.spec_source = &src;
-  const nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr};
+  nsg::DevicePools pools{nullptr, nullptr, nullptr, nullptr, 0};
+  if (nsg::is_grid_kind(s.env_kind)) pools.grid_n_start = nsg::resolve_start_cells(&s);
   const nsg::LaunchOp op = rollout ? nsg::OP_ROLLOUT : nsg::OP_STEP;
   io.k_steps = 1;
   io.gamma = 1.f;

@@ -11,6 +11,21 @@
 
 namespace nsg {
 
+static_assert(kGridTabWords == GRID_TAB_TOTAL_WORDS, "nsgym_host.h: kGridTabWords");
+
+static bool is_start_cell(const NsgymSpec& spec, int c) {
+  if (spec.cell_class) return spec.cell_class[c] == NSGYM_CELL_START;
+  return c < 64 && ((spec.start_mask >> c) & 1ull);
+}
+int resolve_start_cells(NsgymSpec* spec) {
+  if (spec->start_cell >= 0) return 1;
+  int n = 0, first = 0;
+  for (int c = spec->nrow * spec->ncol - 1; c >= 0; --c)
+    if (is_start_cell(*spec, c)) { ++n; first = c; }
+  spec->start_cell = first;
+  return n > 0 ? n : 1;
+}
+
 template <int MAXP>
 static GridProgram<MAXP> build_grid_program(const NsgymSpec& spec, const DevicePools& pools) {
   GridProgram<MAXP> G{};
@@ -20,6 +35,8 @@ static GridProgram<MAXP> build_grid_program(const NsgymSpec& spec, const DeviceP
   G.tab = pools.grid_tab;
   G.nrow = spec.nrow; G.ncol = spec.ncol;
   G.n_cells = spec.nrow * spec.ncol;
+  // several start cells (FrozenLake): a reset samples one; the list is in the map table (resolve_start_cells)
+  G.n_start = pools.grid_n_start > 1 ? pools.grid_n_start : 1;
   G.start_cell = spec.start_cell;
   G.n_dist = spec.n_dist; G.split_mode = spec.split_mode; G.terminal_cliff = spec.terminal_cliff;
   G.reward_f = spec.reward_f; G.reward_h = spec.reward_h; G.reward_g = spec.reward_g; G.reward_s = spec.reward_s;
@@ -379,6 +396,11 @@ int build_grid_tables(const NsgymSpec& spec, uint32_t* words, char* err, size_t 
     const float r = (c & CELL_HOLE) ? spec.reward_h : (c & CELL_GOAL) ? spec.reward_g : (c & CELL_START) ? spec.reward_s : spec.reward_f;
     std::memcpy(words + GRID_TAB_WORDS + c, &r, 4);
   }
+  uint8_t starts[GRID_MAX_CELLS] = {};       // the start cells in row-major order (categorical_sample's cumsum order)
+  int n_start = 0;
+  for (int c = 0; c < n; ++c)
+    if (is_start_cell(spec, c)) starts[n_start++] = uint8_t(c);
+  std::memcpy(words + GRID_TAB_START_WORD, starts, sizeof starts);
   return GRID_TAB_TOTAL_WORDS;
 }
 

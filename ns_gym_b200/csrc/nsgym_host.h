@@ -18,10 +18,16 @@ struct DevicePools {
   const int32_t* pool_i;
   const uint32_t* bitmap;
   const uint32_t* grid_tab;   // gridworld map tables (nsgym_grid.cuh: next[4 n] ++ cls[n]), NULL for classic control
+  int32_t grid_n_start;       // > 1: a reset samples one of the map's start cells (listed in grid_tab)
 };
 
 // Map tables of a gridworld spec, as the kernels read them (host side; nsgym_create uploads them).
-// Returns the number of 32-bit words written to `words` (capacity 328), or -1 with `err` set.
+// Returns the number of 32-bit words written to `words` (capacity kGridTabWords), or -1 with `err` set.
+constexpr int kGridTabWords = 392;    // = GRID_TAB_TOTAL_WORDS (nsgym_grid.cuh; asserted in nsgym_gridworld.cu)
+// A spec with start_cell == -1 (FrozenLake map with several 'S' cells, toy_text.py:314-319 accepts any desc):
+// returns the number of start cells and replaces start_cell by the first one; 1 otherwise.  Needs the map
+// (masks / cell_class), i.e. runs before nsgym_create drops the host pointers.
+int resolve_start_cells(NsgymSpec* spec);
 int build_grid_tables(const NsgymSpec& spec, uint32_t* words, char* err, size_t err_len);
 
 // Per-env rows of a heterogeneous handle (nsgym_create_rows): lowered, only the words that vary

@@ -368,6 +368,13 @@ CASES = {
         make=dict(desc=["SFFFFFFFFFFF", "FFFHFFFFFHFF", "FFFFFFFFFFFF", "FHFFFFHFFFFF", "FFFFFFFFFFHF", "FFFFHFFFFFFF",
                         "FFFFFFFFFFFF", "FFHFFFFFHFFF", "FFFFFFFFFFFF", "FFFFFHFFFFFF", "FHFFFFFFFHFF", "FFFFFFFFFFFG"],
                   max_episode_steps=60), steps=150),
+    "frozenlake5_multi_start": _c(
+        # three 'S' cells: every reset samples the start cell (categorical_sample over initial_state_distrib);
+        # short episodes so that each env resets several times
+        "FrozenLake-v1",
+        lambda S, U: {"P": U.DistributionDecrementUpdate(S.ContinuousScheduler(), k=0.03)},
+        wrapper=dict(initial_prob_dist=[0.9, 0.05, 0.05], change_notification=True, delta_change_notification=True),
+        make=dict(desc=["SFFFS", "FHFHF", "FFFFF", "HFFFH", "SFFFG"], max_episode_steps=9), steps=90),
     "bridge_stepwise": _c(
         "ns_gym/Bridge-v0",
         lambda S, U: {"P": U.DistributionStepWiseUpdate(

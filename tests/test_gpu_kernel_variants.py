@@ -99,6 +99,7 @@ SPECIALISING = ["c1_cartpole_readme", "cartpole_silent", "cartpole_persistent", 
 SPECIALISING_SLOW = ["cartpole_lists", "cartpole_stochastic", "cartpole_stochastic_scheds", "cartpole_custom_sched",
                      "cartpole_memoryless_lists", "cartpole_all_params"]
 SPECIALISING_GRID = ["c2_frozenlake8_drift", "c2_frozenlake8_stepchange", "frozenlake8_lerp", "frozenlake8_cyclic_stale",
+                     "frozenlake5_multi_start",
                      "cliff_terminal", "cliff_drift", "c5_bridge_uniform", "c5_bridge_split", "bridge_stepwise"]
 
 
@@ -213,7 +214,7 @@ def test_specialised_row_kernels_equal_precompiled_row_kernels(name, precision):
 
 @pytest.mark.parametrize("n", [(1 << 21) + 100, 1 << 21, (1 << 21) + 101])
 @pytest.mark.parametrize("name", ["c5_bridge_uniform", "c2_frozenlake8_stepchange", "frozenlake8_cyclic_stale",
-                                  "cliff_drift", "bridge_stepwise"])
+                                  "cliff_drift", "bridge_stepwise", "frozenlake5_multi_start"])
 def test_tiled_gridworld_kernels_equal_precompiled_kernels(name, n):
     """Batches of >= 2^21 envs run the tiled specialised kernel (TMA bulk copies prefetch the planes of the
     next tiles into shared memory) on their full tiles of 256 envs and the one-thread-one-env kernel on the

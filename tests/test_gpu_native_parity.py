@@ -44,6 +44,7 @@ LEAN_FP64 = [("c1_cartpole_readme", "LEAN_FAST"), ("cartpole_silent", "LEAN_FAST
              ("mountaincar_continuous", "LEAN_FAST"), ("mountaincar_constraint", "LEAN_FAST"),
              ("pendulum_all", "LEAN_MEDIUM"), ("cartpole_stochastic", "GENERAL"), ("cartpole_stochastic_scheds", "GENERAL"),
              ("c2_frozenlake8_stepchange", "LEAN_FAST"), ("c2_frozenlake8_drift", "LEAN_FAST"), ("cliff_drift", "LEAN_FAST"),
+             ("frozenlake5_multi_start", "LEAN_FAST"),
              ("c5_bridge_uniform", "LEAN_FAST"), ("c5_bridge_split", "LEAN_FAST"),
              ("frozenlake4_random_categorical", "GENERAL"), ("bridge_lipschitz_bounded", "GENERAL"),
              ("c4_cartpole_rows", "ROWS_LEAN"), ("het_cartpole_lean", "ROWS_LEAN"), ("c4_frozenlake8_rows", "ROWS_LEAN")]

@@ -148,3 +148,34 @@ def test_slot_streams_follow_the_spawn_structure_of_the_reference():
     first_draw = two[0][0] - 9.8
     assert torch.allclose(replay[3][0] - 9.8, first_draw, rtol=0, atol=1e-12)
     assert not torch.allclose(cont[3][0] - 9.8, first_draw, rtol=0, atol=1e-12)
+
+
+def test_start_cells_of_a_multi_start_map_are_sampled_uniformly():
+    """FrozenLake map with three 'S' cells (toy_text.py:314-319 accepts any desc): explicit resets and next-step
+    autoresets draw the start cell with categorical_sample over the start cells -- uniform frequencies, only
+    start cells, independent of the previous cell; same cells from the specialised kernel."""
+    import numpy as np
+    import torch
+
+    n = 1 << 16
+    cells = {}
+    for specialize in (0, 1):
+        env = _env("frozenlake5_multi_start", n, precision="fp64")
+        env.set_option("specialize", specialize)
+        env.reset(seed=4)
+        first = env.buffers["state"].clone()
+        counts = np.bincount(first.cpu().numpy(), minlength=25)
+        assert set(np.nonzero(counts)[0]) == {0, 4, 20}
+        assert np.all(np.abs(counts[[0, 4, 20]] / n - 1 / 3) < 0.01), counts[[0, 4, 20]]
+        a = torch.ones(n, dtype=torch.int32, device=env.device)
+        seen = []
+        for _ in range(40):
+            env.step_raw(a)
+            was_reset = (env.buffers["flags"] & 4) != 0
+            seen.append(env.buffers["state"][was_reset].clone())
+        again = torch.cat(seen).cpu().numpy()
+        c2 = np.bincount(again, minlength=25)
+        assert len(again) > n and set(np.nonzero(c2)[0]) == {0, 4, 20}
+        assert np.all(np.abs(c2[[0, 4, 20]] / len(again) - 1 / 3) < 0.01), c2[[0, 4, 20]]
+        cells[specialize] = (first, again)
+    assert torch.equal(cells[0][0], cells[1][0]) and np.array_equal(cells[0][1], cells[1][1])
