@@ -605,6 +605,12 @@ def run_gpu(args):
             roofline["note"] = ("DRAM traffic is below the algorithmic bytes (unchanged theta planes are not written "
                                 "back): achieved / frac are the physical DRAM rate (ncu traffic / CUDA-event time); "
                                 "*_algorithmic keep SURVEY 8(d)'s formula")
+    if roofline["frac"] > 1.0 and "note" not in roofline:
+        roofline["note"] = ("frac > 1: `peak` is the rate of a COPY kernel on this pool (MEASURED_PEAKS.json), not the DRAM "
+                            "ceiling -- ncu puts this kernel at 78.6 % of the theoretical 8.18 TB/s "
+                            "(profiles/r2_full_c1_cartpole_spec.txt); physical DRAM traffic is "
+                            f"{(traffic or 0) / max(n_envs, 1):.1f} B per env-step against {bytes_per_launch_env:.0f} B "
+                            "algorithmic (frac_physical)")
     if len(shards) > 1:
         roofline["note"] = ("heterogeneous batch: one launch per env kind per step; bytes include the per-env row "
                             "words read each step: " +
