@@ -288,3 +288,38 @@ def test_specialised_general_class_gridworld_kernels_equal_precompiled_kernels(n
     for k, (x, y) in enumerate(zip(spec, pre)):
         for key in x:
             assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+
+
+@pytest.mark.parametrize("in_sim_change", [False, True])
+@pytest.mark.parametrize("name,precision", [("c1_cartpole_readme", "fp64"), ("cartpole_persistent", "fp64"),
+                                            ("c5_bridge_uniform", "fp64"), ("c3_pendulum", "fp64")])
+def test_specialised_kernels_on_planning_copies(name, precision, in_sim_change):
+    """A planning copy is not a root env: its TimeLimit counts from the copy (plan_elapsed) and, with
+    in_sim_change False, its parameters are frozen (skip_updates) -- launch facts the specialised kernels keep
+    as run-time values (SpecFix::root = -1).  Steps and fused rollouts of a copy: specialised = precompiled."""
+    import torch
+
+    from tests import parity_util as pu
+
+    case = dict(CASES[name])
+    case["wrapper"] = dict(case.get("wrapper", {}), in_sim_change=in_sim_change)
+    out = {}
+    for specialize in (0, 1):
+        root = pu.gpu_env(case, 512, precision=precision)
+        root.reset(seed=3)
+        for _ in range(5):
+            root.step_raw(root.action_space.sample() * 0)
+        plan = root.get_planning_env(fanout=4, seed=99)
+        plan.set_option("specialize", specialize)
+        a = plan.action_space.sample() * 0
+        for _ in range(6):
+            plan.step_raw(a)
+        assert plan.last_kernel_specialized == bool(specialize)
+        mid = {k: v.clone() for k, v in plan.buffers.items() if v is not None}
+        ret, length = plan.rollout(12, gamma=0.97)
+        assert plan.last_kernel_specialized == bool(specialize)
+        out[specialize] = (mid, {k: v.clone() for k, v in plan.buffers.items() if v is not None}, ret.clone(), length.clone())
+    for part in (0, 1):
+        for key in out[0][part]:
+            assert torch.equal(out[0][part][key], out[1][part][key]), f"{name}: {key} differs ({'steps' if part == 0 else 'rollout'})"
+    assert torch.equal(out[0][2], out[1][2]) and torch.equal(out[0][3], out[1][3])
