@@ -127,7 +127,8 @@ static std::string spec_grid_step_rows_source(const GridProgram<MAXP>& G, const 
 
 // K fused steps of a lean gridworld program under the uniform-random policy (grid_rollout_body)
 template <int KIND, int D, int MAXP>
-static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root, bool slow = false) {
+static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const StepIO<double>& io, bool root, bool slow = false,
+                                            bool tab = false) {
   const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
   std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G);
   s += "extern \"C\" __global__ void __launch_bounds__(256)\nnsgym_spec_grid_rollout(const __grid_constant__ nsg::StepIO<double> io, "
@@ -136,7 +137,8 @@ static std::string spec_grid_rollout_source(const GridProgram<MAXP>& G, const St
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n"
        "  const nsg::HetT<double, " + std::to_string(MAXP) + "> no_rows{};\n"
        "  nsg::grid_rollout_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
-       ", " + (slow ? "true" : "false") + ", false, false, nsg::SpecFix>(G, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, nullptr, 0);\n}\n";
+       ", " + (slow ? "true" : "false") + ", false, " + (tab ? "true" : "false") +
+       ", nsg::SpecFix>(G, no_rows, io, ra.k_steps, ra.gamma, ra.ret, ra.len, static_cast<const uint8_t*>(ra.pol), ra.pol_per_env);\n}\n";
   return s;
 }
 
@@ -246,19 +248,20 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
       return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3((rest.count + block - 1) / block), dim3(block), args, 0, stream);
     }
   }
-  if (op == OP_ROLLOUT && spec_ok && !a.policy && (a.specialize || a.spec_source)) {
+  if (op == OP_ROLLOUT && spec_ok && (a.specialize || a.spec_source)) {
     const bool root = a.plan_elapsed < 0 && !a.skip_updates;
-    const uint32_t facts = spec_facts(io, root) | 64u | (slow ? 1024u : 0u);
+    const bool tab = a.policy != nullptr;            // tabular policy (nsgym_rollout_linear on a gridworld)
+    const uint32_t facts = spec_facts(io, root) | 64u | (slow ? 1024u : 0u) | (tab ? 128u : 0u);
     cudaKernel_t k = nullptr;
     if (a.spec_source || !a.spec_cache || !a.spec_cache->find(facts, &k)) {
-      const std::string src = spec_grid_rollout_source<KIND, D, MAXP>(G, io, root, slow);
+      const std::string src = spec_grid_rollout_source<KIND, D, MAXP>(G, io, root, slow, tab);
       if (a.spec_source) { *a.spec_source = src; return cudaSuccess; }
       k = jit::kernel(src, "nsgym_spec_grid_rollout", false, nullptr);
       if (a.spec_cache) a.spec_cache->put(facts, k);
     }
     if (k) {
       GridPtrs ptrs{G.base.pool_f, G.base.pool_i, G.base.bitmap, G.tab};
-      RolloutArgs ra{a.k_steps, a.gamma, a.ret, a.len, nullptr, 0};
+      RolloutArgs ra{a.k_steps, a.gamma, a.ret, a.len, a.policy, a.policy_per_env};
       void* args[] = {const_cast<StepIO<double>*>(&io), &ptrs, &ra};
       if (a.specialized) *a.specialized = 1;
       return cudaLaunchKernel(reinterpret_cast<const void*>(k), dim3(grid), dim3(block), args, 0, stream);

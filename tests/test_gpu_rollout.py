@@ -180,18 +180,19 @@ def _linear_actions(w, obs, box):
     return v[:, 0] if box else np.argmax(v, axis=1).astype(np.int32)
 
 
+@pytest.mark.parametrize("specialize", [0, 1])
 @pytest.mark.parametrize("name,precision,box,per_env", [
     ("c1_cartpole_readme", "fp32", False, False), ("c1_cartpole_readme", "fp64", False, True),
     ("c3_acrobot", "fp32", False, True), ("c3_mountaincar", "fp64", False, False),
     ("c3_pendulum", "fp32", True, True), ("mountaincar_continuous", "fp64", True, False)])
-def test_linear_policy_rollout_equals_single_steps(name, precision, box, per_env):
+def test_linear_policy_rollout_equals_single_steps(name, precision, box, per_env, specialize):
     """nsgym_rollout_linear: K fused steps under a device-side linear policy on the float32
     observation = K launches with the actions a host restatement of that policy picks."""
     import torch
 
     case, n, K, seed = CASES[name], 2048, 33, 4321
-    a = _make(case, n, precision, seed)
-    b = _make(case, n, precision, seed)
+    a = _make(case, n, precision, seed, specialize=specialize)
+    b = _make(case, n, precision, seed, specialize=specialize)
     r = np.random.default_rng([5, len(name), int(per_env)])
     shape = a.policy_shape(per_env)
     w = r.normal(0, 1, shape).astype(np.float32)
@@ -199,6 +200,7 @@ def test_linear_policy_rollout_equals_single_steps(name, precision, box, per_env
         w *= np.float32(0.5)
     wt = torch.as_tensor(w, device=a.device)
     ret, length = a.rollout(K, gamma=1.0, policy=wt)
+    assert a.last_kernel_specialized == bool(specialize)
     acc = torch.zeros(n, dtype=torch.float32, device=b.device)
     for _ in range(K):
         obs = b.observation().float().cpu().numpy()
@@ -212,18 +214,20 @@ def test_linear_policy_rollout_equals_single_steps(name, precision, box, per_env
     assert torch.equal(ret, acc)
 
 
+@pytest.mark.parametrize("specialize", [0, 1])
 @pytest.mark.parametrize("name,per_env", [("c5_bridge_uniform", False), ("c2_frozenlake8_drift", True),
                                           ("cliff_terminal", False)])
-def test_tabular_policy_rollout_equals_single_steps(name, per_env):
+def test_tabular_policy_rollout_equals_single_steps(name, per_env, specialize):
     """Gridworlds: the linear policy on the one-hot cell is an action table."""
     import torch
 
     case, n, K, seed = CASES[name], 2048, 41, 99
-    a = _make(case, n, "fp64", seed)
-    b = _make(case, n, "fp64", seed)
+    a = _make(case, n, "fp64", seed, specialize=specialize)
+    b = _make(case, n, "fp64", seed, specialize=specialize)
     r = np.random.default_rng([6, len(name)])
     table = r.integers(0, 4, a.policy_shape(per_env)).astype(np.uint8)
     ret, length = a.rollout(K, gamma=1.0, policy=torch.as_tensor(table, device=a.device))
+    assert a.last_kernel_specialized == bool(specialize)
     acc = torch.zeros(n, dtype=torch.float32, device=b.device)
     rows = np.arange(n)
     for _ in range(K):
