@@ -386,8 +386,13 @@ int nsgym_eval_draws(NsgymHandle* h, int what, int lane, int t, double p, uint64
  * constant-bank loads, uniform branches, range / modulo tests and select masks fold away.  Same results as
  * the precompiled lean kernel (bit for bit in fp64 mode; fp32 may differ in the last bit where the folded
  * constants change an FMA contraction).  -1 (default): batches of >= 32768 envs; 0: never; 1: always.
- * Environment: NSGYM_B200_NO_JIT=1 disables it process-wide, NSGYM_B200_NVRTC names libnvrtc.so.12,
- * NSGYM_B200_JIT_VERBOSE=1 prints why a specialisation was not possible (the precompiled kernel runs then). */
+ * Programs with slow-class slots specialise as well (general kernel class, slow class unrolled over the slots);
+ * injected tables, NSGYM_OPT_GENERAL_KERNELS and non-lean per-env rows keep the precompiled kernels.  Gridworld
+ * batches of >= 2^21 envs with 16-byte aligned planes run a tiled variant whose env records arrive in shared
+ * memory through TMA bulk copies (NSGYM_B200_NO_TILED=1 turns it off).
+ * Environment: NSGYM_B200_NO_JIT=1 disables it process-wide, NSGYM_B200_NVRTC names libnvrtc.so.12 ("none": act
+ * as if absent), NSGYM_B200_JIT_VERBOSE=1 prints why a specialisation was not possible (the precompiled kernel
+ * runs then), NSGYM_B200_JIT_DUMP=dir keeps the generated sources and cubins. */
 enum { NSGYM_OPT_GENERAL_KERNELS = 1, NSGYM_OPT_SPECIALIZE = 2 };
 int nsgym_set_option(NsgymHandle* h, int option, int64_t value);
 /* 1 when the handle's last step / rollout launch went to a program-specialised kernel */
