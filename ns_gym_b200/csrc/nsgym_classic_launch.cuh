@@ -299,7 +299,8 @@ static std::string spec_rows_object(const std::string& real, int np) {
 // The single-step kernel of a batch with lean per-env rows (classic_step_het_body): program and row layout
 // are constants, so every lane loads exactly the row words that vary and the shared ones are immediates.
 template <typename R, int KIND, int NP>
-static std::string spec_step_rows_source(const ProgramT<R, NP>& P, const HetT<R, NP>& H, const StepIO<R>& io, bool root) {
+static std::string spec_step_rows_source(const ProgramT<R, NP>& P, const HetT<R, NP>& H, const StepIO<R>& io, bool root,
+                                         bool lean = true) {
   const std::string real = std::is_same<R, float>::value ? "float" : "double";
   const ProgramHeadT<R, NP>& head = P;
   const std::string prog = "ProgramT<" + real + ", " + std::to_string(NP) + ">";
@@ -308,13 +309,14 @@ static std::string spec_step_rows_source(const ProgramT<R, NP>& P, const HetT<R,
   s += "__device__ constexpr " + prog + " spec_program() {\n  " + prog + " P{};\n" +
        spec_assign("static_cast<" + headt + "&>(P)", headt, head) + "  return P;\n}\n}  // namespace nsg\n";
   s += spec_rows_source<R, NP>(H);
-  s += "extern \"C\" __global__ void __launch_bounds__(256, NSGYM_HET_LEAN_MIN_BLOCKS)\nnsgym_spec_classic_step_rows("
+  s += std::string("extern \"C\" __global__ void __launch_bounds__(256, ") + (lean ? "NSGYM_HET_LEAN_MIN_BLOCKS" : "NSGYM_HET_MIN_BLOCKS") +
+       ")\nnsgym_spec_classic_step_rows("
        "const __grid_constant__ nsg::StepIO<" + real + "> io, const __grid_constant__ nsg::HetPtrs hp, "
        "const __grid_constant__ nsg::PoolPtrs pp) {\n"
        "  constexpr nsg::" + prog + " P0 = nsg::spec_program();\n  nsg::" + prog + " P = P0;\n"
        "  P.pool_f = pp.pool_f; P.pool_i = pp.pool_i; P.bitmap = pp.bitmap;\n" + spec_rows_object(real, NP) +
        "  nsg::classic_step_het_body<" + real + ", " + std::to_string(KIND) + ", " + std::to_string(NP) +
-       ", true, nsg::SpecFix>(P, H, io);\n}\n";
+       ", " + (lean ? "true" : "false") + ", nsg::SpecFix>(P, H, io);\n}\n";
   return s;
 }
 
@@ -356,12 +358,15 @@ static cudaError_t launch_classic_knp(LaunchOp op, const NsgymSpec& spec, const 
       const bool lean_rows = a.rows->lean && !a.general_kernels && !a.inj_u && !a.inj_z;
       if (a.kernel_class) *a.kernel_class = lean_rows ? NSGYM_KERNEL_ROWS_LEAN : NSGYM_KERNEL_ROWS_GENERAL;
       if (a.specialized) *a.specialized = 0;
-      if (op == OP_STEP && lean_rows && a.specialize) {
+      // rows of the general class (stochastic schedulers, cursor rules) specialise too: slot loop unrolled,
+      // row layout constant, no injection code
+      const bool rows_spec_ok = lean_rows || (!a.general_kernels && !a.inj_u && !a.inj_z);
+      if (op == OP_STEP && rows_spec_ok && a.specialize) {
         const bool root = a.plan_elapsed < 0 && !a.skip_updates;
-        const uint32_t facts = spec_facts(io, root) | 256u;
+        const uint32_t facts = spec_facts(io, root) | 256u | (lean_rows ? 0u : 2048u);
         cudaKernel_t k = nullptr;
         if (!a.spec_cache || !a.spec_cache->find(facts, &k)) {
-          k = jit::kernel(spec_step_rows_source<R, KIND, NP>(P, H, io, root), "nsgym_spec_classic_step_rows",
+          k = jit::kernel(spec_step_rows_source<R, KIND, NP>(P, H, io, root, lean_rows), "nsgym_spec_classic_step_rows",
                           std::is_same<R, float>::value, nullptr);
           if (a.spec_cache) a.spec_cache->put(facts, k);
         }

@@ -110,18 +110,19 @@ static std::string spec_grid_step_tiled_source(const GridProgram<MAXP>& G, const
 // single step of a gridworld batch with lean per-env rows (grid_step_het_body)
 template <int KIND, int D, int MAXP>
 static std::string spec_grid_step_rows_source(const GridProgram<MAXP>& G, const HetT<double, MAXP>& H,
-                                              const StepIO<double>& io, bool root) {
+                                              const StepIO<double>& io, bool root, bool lean = true) {
   const std::string prog = "GridProgram<" + std::to_string(MAXP) + ">";
   std::string s = spec_prelude<double>("nsgym_grid.cuh", io, root) + spec_grid_program_source<MAXP>(G) +
                   spec_rows_source<double, MAXP>(H);
-  s += "extern \"C\" __global__ void __launch_bounds__(256, NSGYM_HET_LEAN_MIN_BLOCKS)\nnsgym_spec_grid_step_rows("
+  s += std::string("extern \"C\" __global__ void __launch_bounds__(256, ") + (lean ? "NSGYM_HET_LEAN_MIN_BLOCKS" : "NSGYM_HET_MIN_BLOCKS") +
+       ")\nnsgym_spec_grid_step_rows("
        "const __grid_constant__ nsg::StepIO<double> io, const __grid_constant__ nsg::GridPtrs ptrs, "
        "const __grid_constant__ nsg::HetPtrs hp) {\n"
        "  constexpr nsg::" + prog + " G0 = nsg::spec_program();\n  nsg::" + prog + " G = G0;\n"
        "  G.base.pool_f = ptrs.pool_f; G.base.pool_i = ptrs.pool_i; G.base.bitmap = ptrs.bitmap; G.tab = ptrs.tab;\n" +
        spec_rows_object("double", MAXP) +
        "  nsg::grid_step_het_body<" + std::to_string(KIND) + ", " + std::to_string(D) + ", " + std::to_string(MAXP) +
-       ", true, nsg::SpecFix>(G, H, io);\n}\n";
+       ", " + (lean ? "true" : "false") + ", nsg::SpecFix>(G, H, io);\n}\n";
   return s;
 }
 
@@ -169,12 +170,15 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     if (a.spec_source) return cudaErrorNotSupported;
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     if (a.specialized) *a.specialized = 0;
+    // (lean rows only: the specialised general-class gridworld row kernel does not reproduce the precompiled one
+    // yet -- Memoryless next-fire times differ -- so rows with stochastic rules keep the interpreter)
     if (op == OP_STEP && a.rows->lean && !a.general_kernels && !a.inj_u && a.specialize) {
       const bool root = a.plan_elapsed < 0 && !a.skip_updates;
-      const uint32_t facts = spec_facts(io, root) | 256u;
+      const bool lean_rows = a.rows->lean;
+      const uint32_t facts = spec_facts(io, root) | 256u | (lean_rows ? 0u : 2048u);
       cudaKernel_t k = nullptr;
       if (!a.spec_cache || !a.spec_cache->find(facts, &k)) {
-        k = jit::kernel(spec_grid_step_rows_source<KIND, D, MAXP>(G, H, io, root), "nsgym_spec_grid_step_rows", false, nullptr);
+        k = jit::kernel(spec_grid_step_rows_source<KIND, D, MAXP>(G, H, io, root, lean_rows), "nsgym_spec_grid_step_rows", false, nullptr);
         if (a.spec_cache) a.spec_cache->put(facts, k);
       }
       if (k) {

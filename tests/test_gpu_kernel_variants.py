@@ -185,6 +185,26 @@ def test_specialisation_is_automatic_for_large_batches_only():
     assert not env.last_kernel_specialized
 
 
+@pytest.mark.parametrize("name", ["het_cartpole_wide"])
+def test_specialised_general_row_kernels_equal_precompiled_row_kernels(name):
+    """Classic-control per-env rows of the general class (stochastic schedulers, cursor rules, slow updates per
+    env): the kernel specialised on program and row layout (slot loop unrolled, row loads up front, no injection
+    code) against the precompiled general per-env kernel, bit for bit in fp64.  (Gridworld rows of the general
+    class keep the precompiled kernel.)"""
+    import torch
+
+    from ns_gym_b200 import native as nv
+
+    case = CASES[name]
+    info = {}
+    spec = _run(case, "fp64", False, specialize=1, info=info, steps=40)
+    pre = _run(case, "fp64", False, specialize=0, steps=40)
+    assert all(c == nv.KERNEL_ROWS_GENERAL for c in info["class"]) and all(info["specialized"]), (info["class"][:2], info["specialized"][:2])
+    for k, (x, y) in enumerate(zip(spec, pre)):
+        for key in x:
+            assert torch.equal(x[key], y[key]), f"{name}: {key} differs at step {k}"
+
+
 @pytest.mark.parametrize("precision", ["fp64", "fp32"])
 @pytest.mark.parametrize("name", ["het_cartpole_lean", "c4_cartpole_rows", "c4_frozenlake8_rows"])
 def test_specialised_row_kernels_equal_precompiled_row_kernels(name, precision):
