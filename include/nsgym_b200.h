@@ -387,7 +387,7 @@ int nsgym_eval_draws(NsgymHandle* h, int what, int lane, int t, double p, uint64
  * the precompiled lean kernel (bit for bit in fp64 mode; fp32 may differ in the last bit where the folded
  * constants change an FMA contraction).  -1 (default): batches of >= 32768 envs; 0: never; 1: always.
  * Programs with slow-class slots specialise as well (general kernel class, slow class unrolled over the slots);
- * injected tables, NSGYM_OPT_GENERAL_KERNELS and non-lean per-env rows keep the precompiled kernels.  Gridworld
+ * so do per-env rows of either class; injected tables and NSGYM_OPT_GENERAL_KERNELS keep the precompiled kernels.  Gridworld
  * batches of >= 2^21 envs with 16-byte aligned planes run a tiled variant whose env records arrive in shared
  * memory through TMA bulk copies (NSGYM_B200_NO_TILED=1 turns it off).
  * Environment: NSGYM_B200_NO_JIT=1 disables it process-wide, NSGYM_B200_NVRTC names libnvrtc.so.12 ("none": act

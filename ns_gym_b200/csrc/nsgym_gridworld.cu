@@ -170,9 +170,9 @@ static cudaError_t launch_grid_k(LaunchOp op, const NsgymSpec& spec, const Devic
     if (a.spec_source) return cudaErrorNotSupported;
     const HetT<double, MAXP> H = build_het_by_index<MAXP>(spec, *a.rows);
     if (a.specialized) *a.specialized = 0;
-    // (lean rows only: the specialised general-class gridworld row kernel does not reproduce the precompiled one
-    // yet -- Memoryless next-fire times differ -- so rows with stochastic rules keep the interpreter)
-    if (op == OP_STEP && a.rows->lean && !a.general_kernels && !a.inj_u && a.specialize) {
+    // rows of the general class (stochastic schedulers per env) specialise too: row layout constant, row loads up
+    // front, no injection code
+    if (op == OP_STEP && !a.general_kernels && !a.inj_u && a.specialize) {
       const bool root = a.plan_elapsed < 0 && !a.skip_updates;
       const bool lean_rows = a.rows->lean;
       const uint32_t facts = spec_facts(io, root) | 256u | (lean_rows ? 0u : 2048u);

@@ -185,17 +185,32 @@ def test_specialisation_is_automatic_for_large_batches_only():
     assert not env.last_kernel_specialized
 
 
-@pytest.mark.parametrize("name", ["het_cartpole_wide"])
+def _het_frozenlake_stochastic(S, U, e):
+    """per-env rows of the general class on a gridworld: a stochastic scheduler per env (the Memoryless one
+    seeded: its first transition time is drawn at construction, schedulers.py:92-116)"""
+    r = np.random.default_rng([8, e])
+    if int(r.integers(0, 2)):
+        return {"P": U.DistributionDecrementUpdate(S.RandomScheduler(float(r.uniform(0.2, 0.9))), k=float(r.uniform(0.01, 0.05)))}
+    return {"P": U.UniformDrift(S.MemorylessScheduler(p=float(r.uniform(0.2, 0.6)), seed=e), rate=float(r.uniform(0.02, 0.1)))}
+
+
+EXTRA_CASES = {
+    "het_frozenlake_stochastic": dict(env_id="FrozenLake-v1", params_of=_het_frozenlake_stochastic,
+                                      wrapper=dict(initial_prob_dist=[0.9, 0.05, 0.05], change_notification=True,
+                                                   delta_change_notification=True), make={}, steps=60),
+}
+
+
+@pytest.mark.parametrize("name", ["het_cartpole_wide", "het_frozenlake_stochastic"])
 def test_specialised_general_row_kernels_equal_precompiled_row_kernels(name):
-    """Classic-control per-env rows of the general class (stochastic schedulers, cursor rules, slow updates per
-    env): the kernel specialised on program and row layout (slot loop unrolled, row loads up front, no injection
-    code) against the precompiled general per-env kernel, bit for bit in fp64.  (Gridworld rows of the general
-    class keep the precompiled kernel.)"""
+    """Per-env rows of the general class (stochastic schedulers, cursor rules, slow updates per env): the kernel
+    specialised on program and row layout (slot loop unrolled, row loads up front, no injection code) against the
+    precompiled general per-env kernel, bit for bit in fp64."""
     import torch
 
     from ns_gym_b200 import native as nv
 
-    case = CASES[name]
+    case = CASES.get(name) or EXTRA_CASES[name]
     info = {}
     spec = _run(case, "fp64", False, specialize=1, info=info, steps=40)
     pre = _run(case, "fp64", False, specialize=0, steps=40)
